@@ -1,0 +1,181 @@
+"""Generate the golden fixtures in this directory from the UNMODIFIED, compiled
+reference (pypmc v1.2.6 @ 9e0ab49).
+
+Run in the build container only (the reference does not travel to the GPU box):
+
+    python -m pip install --no-index --no-build-isolation --no-deps \
+        --find-links /opt/wheelhouse --target baseline/_ref /tmp/refbuild   # copy of /root/reference
+    PYTHONPATH=baseline/_ref python tests/golden/make_golden.py
+
+Every array written here is an output of the reference's own public API
+(``MixtureDensity.multi_evaluate``, ``gaussian_pmc``, ``student_t_pmc``,
+``PMC``, ``GaussianInference``) on seeded synthetic inputs built as SURVEY.md
+section 8(d) prescribes.  The fixtures pin ``oracle/`` (tests/test_oracle.py) and the
+CUDA path (tests/test_gpu_*.py).
+"""
+import os
+import sys
+import logging
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+
+import pypmc  # noqa: E402  (the compiled reference)
+from pypmc.density.mixture import create_gaussian_mixture, create_t_mixture  # noqa: E402
+from pypmc.mix_adapt.pmc import gaussian_pmc, student_t_pmc, PMC  # noqa: E402
+from pypmc.mix_adapt.variational import GaussianInference  # noqa: E402
+
+logging.getLogger("pypmc").setLevel(logging.ERROR)
+assert "baseline/_ref" in pypmc.__file__, pypmc.__file__
+
+
+def synth_mixture(K, D, seed=1, ridge=0.5, spread=3.0):
+    """mu_k ~ N(0, spread^2), Sigma_k = A A^T + ridge*I with A_ij ~ N(0, 1/D),
+    weights ~ U(0.5, 1.5) normalised."""
+    rng = np.random.default_rng(seed)
+    means = rng.normal(0.0, spread, size=(K, D))
+    covs = np.empty((K, D, D))
+    for k in range(K):
+        a = rng.normal(0.0, 1.0 / np.sqrt(D), size=(D, D))
+        covs[k] = a @ a.T + ridge * np.eye(D)
+    w = rng.uniform(0.5, 1.5, size=K)
+    return means, covs, w / w.sum()
+
+
+def synth_samples(N, means, covs, seed=2, dof=None):
+    """component ~ U{0..K-1}, x = mu_c + L_c z [ / sqrt(chi2_nu/nu) ]."""
+    rng = np.random.default_rng(seed)
+    K, D = means.shape
+    comp = rng.integers(0, K, size=N)
+    chol = np.linalg.cholesky(covs)
+    z = rng.normal(size=(N, D))
+    x = np.einsum("nij,nj->ni", chol[comp], z)
+    if dof is not None:
+        x /= np.sqrt(rng.chisquare(dof, size=N) / dof)[:, None]
+    x += means[comp]
+    sw = rng.uniform(0.5, 1.5, size=N)
+    return np.ascontiguousarray(x), comp.astype(np.int64), sw
+
+
+def recover(mix, t=False):
+    out = dict(
+        weights=np.array(mix.weights),
+        means=np.array([c.mu for c in mix.components]),
+        covs=np.array([c.sigma for c in mix.components]),
+    )
+    if t:
+        out["dofs"] = np.array([c.dof for c in mix.components])
+    return out
+
+
+def pack(prefix, d):
+    return {prefix + "_" + k: v for k, v in d.items()}
+
+
+def gauss_case(name, N, K, D, ridge=0.5, dead=(), full=True, keep_rows=None):
+    means, covs, w = synth_mixture(K, D, ridge=ridge)
+    for k in dead:
+        w[k] = 0.0
+    w = w / w.sum()
+    x, latent, sw = synth_samples(N, means, covs)
+    mix = create_gaussian_mixture(means, covs, w)
+    individual = np.empty((N, K))
+    logq = mix.multi_evaluate(x, individual=individual)
+    rows = slice(None) if keep_rows is None else slice(0, keep_rows)  # individual is N x K: keep a prefix
+    out = dict(x=x, latent=latent, sample_weights=sw, means=means, covs=covs, weights=np.array(mix.weights),
+               individual=individual[rows], logq=logq)
+    out.update(pack("pmc_weighted", recover(gaussian_pmc(x, mix, weights=sw))))
+    out.update(pack("pmc_unweighted", recover(gaussian_pmc(x, mix))))
+    p = PMC(x, mix, weights=sw)
+    out["loglik_weighted"] = np.array(p.log_likelihood())
+    out["loglik_unweighted"] = np.array(PMC(x, mix).log_likelihood())
+    if full:
+        out.update(pack("pmc_latent_rb", recover(gaussian_pmc(x, mix, weights=sw, latent=latent, rb=True, mincount=2))))
+        out.update(pack("pmc_latent_nonrb", recover(gaussian_pmc(x, mix, weights=sw, latent=latent, rb=False))))
+        p3 = PMC(x, mix, weights=sw)
+        out["pmc_run3_converged"] = np.array(-1 if (c := p3.run(iterations=3)) is None else c)
+        out.update(pack("pmc_run3", recover(p3.density)))
+        out["pmc_run3_loglik"] = np.array(p3.log_likelihood())
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "cond(cov0) = %.3g" % np.linalg.cond(covs[0]))
+
+
+def student_case(name, N, K, D, dof=4.0, full=True, keep_rows=None):
+    means, covs, w = synth_mixture(K, D)
+    x, latent, sw = synth_samples(N, means, covs, dof=dof)
+    dofs = np.full(K, dof)
+    dofs[0] = 2.5  # not all equal
+    mix = create_t_mixture(means, covs, dofs, w)
+    individual = np.empty((N, K))
+    logq = mix.multi_evaluate(x, individual=individual)
+    rows = slice(None) if keep_rows is None else slice(0, keep_rows)
+    out = dict(x=x, latent=latent, sample_weights=sw, means=means, covs=covs, dofs=dofs,
+               weights=np.array(mix.weights), individual=individual[rows], logq=logq)
+    out.update(pack("pmc_nodof_weighted", recover(student_t_pmc(x, mix, weights=sw, dof_solver_steps=0), True)))
+    out.update(pack("pmc_dof_weighted", recover(student_t_pmc(x, mix, weights=sw), True)))
+    if full:
+        out.update(pack("pmc_nodof_unweighted", recover(student_t_pmc(x, mix, dof_solver_steps=0), True)))
+        out.update(pack("pmc_dof_unweighted", recover(student_t_pmc(x, mix), True)))
+        out.update(pack("pmc_dof_latent_nonrb", recover(student_t_pmc(x, mix, weights=sw, latent=latent, rb=False), True)))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name)
+
+
+VB_ATTRS = ("expectation_gauss_exponent", "log_rho", "r", "N_comp", "inv_N_comp", "x_mean_comp", "S",
+            "expectation_det_ln_lambda", "expectation_ln_pi", "alpha", "beta", "nu", "m", "W", "log_det_W")
+
+
+def vb_snapshot(vb, keep_rows=None):
+    out = {}
+    for a in VB_ATTRS:
+        v = np.array(getattr(vb, a))
+        if keep_rows is not None and v.ndim == 2 and v.shape[0] == vb.N:
+            v = v[:keep_rows]   # N x K attributes: keep a prefix
+        out[a] = v
+    return out
+
+
+def vb_case(name, N, K, D, full=True, keep_rows=None):
+    means, covs, w = synth_mixture(K, D)
+    x, latent, sw = synth_samples(N, means, covs)
+    mix = create_gaussian_mixture(means, covs, w)
+    out = dict(x=x, sample_weights=sw, means=means, covs=covs, weights=np.array(mix.weights))
+    for tag, weights in (("unw", None), ("wgt", sw)):
+        vb = GaussianInference(x, initial_guess=mix, weights=weights)
+        if tag == "wgt" and not full:
+            continue
+        out.update(pack(tag + "_init", vb_snapshot(vb, keep_rows)))
+        out[tag + "_init_bound"] = np.array(vb.likelihood_bound())
+        vb.update()
+        out.update(pack(tag + "_upd1", vb_snapshot(vb, keep_rows)))
+        out[tag + "_upd1_bound"] = np.array(vb.likelihood_bound())
+        vb.update()
+        out[tag + "_upd2_bound"] = np.array(vb.likelihood_bound())
+        out.update(pack(tag + "_upd2_mix", recover(vb.make_mixture())))
+    if not full:
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print(name)
+        return
+    # default initial guess ("first") with explicit component count and pruning run
+    vb = GaussianInference(x, components=K + 2)
+    out["first_init_bound"] = np.array(vb.likelihood_bound())
+    it = vb.run(iterations=5, prune=1.0)
+    out["first_run5_converged"] = np.array(-1 if it is None else it)
+    out["first_run5_K"] = np.array(vb.K)
+    out["first_run5_bound"] = np.array(vb.likelihood_bound())
+    out.update(pack("first_run5", {a: np.array(getattr(vb, a)) for a in ("N_comp", "m", "W", "alpha", "beta", "nu")}))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name)
+
+
+if __name__ == "__main__":
+    gauss_case("gauss_small", N=257, K=5, D=7, dead=(3,))
+    gauss_case("gauss_c2", N=2048, K=32, D=30, full=False, keep_rows=128)  # BASELINE config 2 shape
+    gauss_case("gauss_c2_stress", N=2048, K=32, D=30, ridge=1e-4, full=False, keep_rows=128)  # kappa ~ 3e4
+    student_case("student_small", N=301, K=4, D=5)
+    student_case("student_c4", N=1600, K=16, D=40, full=False, keep_rows=128)  # BASELINE config 4 shape
+    vb_case("vb_small", N=300, K=4, D=3)
+    vb_case("vb_c3", N=2048, K=64, D=20, full=False, keep_rows=64)          # BASELINE config 3 shape
