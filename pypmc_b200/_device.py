@@ -1,0 +1,77 @@
+"""Host <-> device plumbing for the density / mix_adapt classes (torch is used for device memory only)."""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _lib
+
+
+def torch():
+    import torch as _t
+    return _t
+
+
+def is_device_tensor(x) -> bool:
+    return (not isinstance(x, np.ndarray)) and hasattr(x, "is_cuda") and bool(x.is_cuda)
+
+
+def as_samples(x):
+    """Validate a sample matrix with the reference's contract (``np.ndarray[double, ndim=2] not None``,
+    mixture.pyx:112): float64, two-dimensional; numpy (host) or torch CUDA tensor (device resident)."""
+    if x is None:
+        raise TypeError("Argument 'x' must not be None")
+    if is_device_tensor(x):
+        if x.dtype != torch().float64 or x.dim() != 2:
+            raise ValueError("device samples must be a 2-d float64 tensor")
+        return x
+    if not isinstance(x, np.ndarray):
+        raise TypeError("Argument 'x' has incorrect type (expected numpy.ndarray, got %s)" % type(x).__name__)
+    if x.dtype != np.float64:
+        raise ValueError("Buffer dtype mismatch, expected 'double' but got %r" % x.dtype)
+    if x.ndim != 2:
+        raise ValueError("Buffer has wrong number of dimensions (expected 2, got %d)" % x.ndim)
+    return x
+
+
+def row_major(x: np.ndarray):
+    """(array, ldx) of a host sample matrix usable by the C ABI: unit column stride, any row stride."""
+    n, d = x.shape
+    if n == 0:
+        return np.ascontiguousarray(x), d
+    if x.strides[1] == 8 and x.strides[0] >= 8 * d and x.strides[0] % 8 == 0:
+        return x, x.strides[0] // 8
+    x = np.ascontiguousarray(x)
+    return x, d
+
+
+def to_device(a, device=None, dtype=None):
+    t = torch()
+    if a is None:
+        return None
+    if is_device_tensor(a):
+        return a
+    dev = "cuda:%d" % (_lib.default_device() if device is None else device)
+    arr = np.ascontiguousarray(a) if dtype is None else np.ascontiguousarray(a, dtype=dtype)
+    return t.from_numpy(arr).to(dev)
+
+
+def current_stream_ptr() -> int:
+    return torch().cuda.current_stream().cuda_stream
+
+
+class PackedComponents:
+    """Records + output columns of the components to evaluate, on host and (lazily) on device."""
+
+    def __init__(self, records: np.ndarray, cols, weights=None):
+        self.records = np.ascontiguousarray(records, dtype=np.float64)       # [kl, RL]
+        self.cols = np.ascontiguousarray(cols, dtype=np.int32)               # [kl]
+        self.kl = len(self.cols)
+        if weights is not None:
+            # mixture weights live in scalar slot S_WEIGHT (last 8 doubles of a record)
+            self.records[:, self.records.shape[1] - _lib.NUM_SCALARS + _lib.S_WEIGHT] = weights
+        self._dev = None
+
+    def device(self):
+        if self._dev is None:
+            self._dev = (to_device(self.records), to_device(self.cols))
+        return self._dev

@@ -1,0 +1,406 @@
+// pmcb200.cu -- C ABI (include/pmcb200.h) over the sm_100a kernels K1 (k1_mixture_eval.cuh) and
+// K2 (k2_suffstats.cuh).  No torch types, no CPU fallback: every compute entry point needs a CUDA device.
+#include "../../include/pmcb200.h"
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "k1_dispatch.cuh"
+#include "k2_suffstats.cuh"
+#include "microbench.cuh"
+
+namespace pmc {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+int k1_launch(int dp, const EvalArgs& a, int grid, cudaStream_t stream) {
+  switch (dp) {
+#define PMC_CASE(DP) \
+  case DP:           \
+    return k1_launch_dp<DP>(a, grid, stream);
+    PMC_CASE(2) PMC_CASE(4) PMC_CASE(6) PMC_CASE(8) PMC_CASE(10) PMC_CASE(12) PMC_CASE(14) PMC_CASE(16)
+    PMC_CASE(18) PMC_CASE(20) PMC_CASE(22) PMC_CASE(24) PMC_CASE(26) PMC_CASE(28) PMC_CASE(30) PMC_CASE(32)
+    PMC_CASE(34) PMC_CASE(36) PMC_CASE(38) PMC_CASE(40) PMC_CASE(42) PMC_CASE(44) PMC_CASE(46) PMC_CASE(48)
+    PMC_CASE(50) PMC_CASE(52) PMC_CASE(54) PMC_CASE(56) PMC_CASE(58) PMC_CASE(60) PMC_CASE(62) PMC_CASE(64)
+#undef PMC_CASE
+    default:
+      return int(cudaErrorInvalidValue);
+  }
+}
+
+template <int DP>
+struct CfgQuery {
+  static int tile() { return EvalCfg<DP>::TS; }
+  static int warps() { return EvalCfg<DP>::NW; }
+};
+
+int k1_tile_rows(int dp) {
+  switch (dp) {
+#define PMC_CASE(DP) \
+  case DP:           \
+    return CfgQuery<DP>::tile();
+    PMC_CASE(2) PMC_CASE(4) PMC_CASE(6) PMC_CASE(8) PMC_CASE(10) PMC_CASE(12) PMC_CASE(14) PMC_CASE(16)
+    PMC_CASE(18) PMC_CASE(20) PMC_CASE(22) PMC_CASE(24) PMC_CASE(26) PMC_CASE(28) PMC_CASE(30) PMC_CASE(32)
+    PMC_CASE(34) PMC_CASE(36) PMC_CASE(38) PMC_CASE(40) PMC_CASE(42) PMC_CASE(44) PMC_CASE(46) PMC_CASE(48)
+    PMC_CASE(50) PMC_CASE(52) PMC_CASE(54) PMC_CASE(56) PMC_CASE(58) PMC_CASE(60) PMC_CASE(62) PMC_CASE(64)
+#undef PMC_CASE
+    default:
+      return 0;
+  }
+}
+
+int k1_warps(int dp) {
+  switch (dp) {
+#define PMC_CASE(DP) \
+  case DP:           \
+    return CfgQuery<DP>::warps();
+    PMC_CASE(2) PMC_CASE(4) PMC_CASE(6) PMC_CASE(8) PMC_CASE(10) PMC_CASE(12) PMC_CASE(14) PMC_CASE(16)
+    PMC_CASE(18) PMC_CASE(20) PMC_CASE(22) PMC_CASE(24) PMC_CASE(26) PMC_CASE(28) PMC_CASE(30) PMC_CASE(32)
+    PMC_CASE(34) PMC_CASE(36) PMC_CASE(38) PMC_CASE(40) PMC_CASE(42) PMC_CASE(44) PMC_CASE(46) PMC_CASE(48)
+    PMC_CASE(50) PMC_CASE(52) PMC_CASE(54) PMC_CASE(56) PMC_CASE(58) PMC_CASE(60) PMC_CASE(62) PMC_CASE(64)
+#undef PMC_CASE
+    default:
+      return 0;
+  }
+}
+
+// sums[0..1] = fixed-order sum of the per-warp partial pairs
+__global__ void k1_reduce_sums(const double* __restrict__ partials, int count, double* __restrict__ sums) {
+  double a = 0.0, w = 0.0;
+  for (int i = threadIdx.x; i < count; i += 32) {
+    a += partials[2 * i];
+    w += partials[2 * i + 1];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    w += __shfl_xor_sync(0xffffffffu, w, o);
+  }
+  if (threadIdx.x == 0) {
+    sums[0] = a;
+    sums[1] = w;
+  }
+}
+
+}  // namespace pmc
+
+using namespace pmc;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+struct pmcb200_ctx {
+  int device = 0;
+  int sm_count = 0;
+  DevBuf ws;              // partial sums of K1 / K2 (device-pointer entry points)
+  cudaStream_t copy_stream[2] = {nullptr, nullptr};
+  // host pipeline: per-slot device buffers
+  DevBuf hx[2], hw[2], hlogq[2], hlp[2], hresp[2], haux[2], hws[2], hsums[2];
+  DevBuf hrec, hcols;
+  int64_t launches = 0;
+};
+
+static int ensure(DevBuf& b, size_t bytes) {
+  if (bytes <= b.bytes) return 0;
+  if (b.p) PMC_CUDA_CHECK(cudaFree(b.p));
+  b.p = nullptr;
+  b.bytes = 0;
+  PMC_CUDA_CHECK(cudaMalloc(&b.p, bytes));
+  b.bytes = bytes;
+  return 0;
+}
+
+extern "C" {
+
+int pmcb200_version(void) { return PMCB200_VERSION; }
+
+const char* pmcb200_last_error(void) { return g_last_error.c_str(); }
+
+int pmcb200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int pmcb200_create(int device, pmcb200_ctx** out) {
+  PMC_REQUIRE(out != nullptr, "pmcb200_create: out is NULL");
+  int n = 0;
+  PMC_CUDA_CHECK(cudaGetDeviceCount(&n));
+  PMC_REQUIRE(device >= 0 && device < n, "pmcb200_create: no such CUDA device (this library has no CPU fallback)");
+  PMC_CUDA_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  PMC_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  PMC_REQUIRE(prop.major >= 10, "pmcb200_create: kernels are built for sm_100a (Blackwell) only");
+  pmcb200_ctx* c = new pmcb200_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  for (int i = 0; i < 2; ++i) PMC_CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream[i], cudaStreamNonBlocking));
+  *out = c;
+  return 0;
+}
+
+int pmcb200_destroy(pmcb200_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  DevBuf* all[] = {&c->ws, &c->hrec, &c->hcols};
+  for (DevBuf* b : all)
+    if (b->p) cudaFree(b->p);
+  for (int i = 0; i < 2; ++i) {
+    DevBuf* slot[] = {&c->hx[i], &c->hw[i], &c->hlogq[i], &c->hlp[i], &c->hresp[i], &c->haux[i], &c->hws[i], &c->hsums[i]};
+    for (DevBuf* b : slot)
+      if (b->p) cudaFree(b->p);
+    if (c->copy_stream[i]) cudaStreamDestroy(c->copy_stream[i]);
+  }
+  delete c;
+  return 0;
+}
+
+int pmcb200_record_len(int d) {
+  if (d < 1 || d > PMCB200_MAX_DIM) return -1;
+  return record_len((d + 1) & ~1);
+}
+
+int pmcb200_pack_record(int d, const double* t, const double* center, const double* scalars, double* rec) {
+  PMC_REQUIRE(d >= 1 && d <= PMCB200_MAX_DIM, "pack_record: dimension must be in 1..64");
+  PMC_REQUIRE(t && center && scalars && rec, "pack_record: NULL argument");
+  const int dp = (d + 1) & ~1, h = dp / 2, nt = tri_len(dp);
+  auto T = [&](int i, int j) -> double { return (i < d && j < d && j <= i) ? t[size_t(i) * d + j] : 0.0; };
+  for (int r = 0; r < h; ++r)
+    for (int p = 0; p <= r; ++p) {
+      double* b = rec + 2 * r * (r + 1) + 4 * p;
+      b[0] = T(2 * r, 2 * p);
+      b[1] = T(2 * r, 2 * p + 1);
+      b[2] = T(2 * r + 1, 2 * p);
+      b[3] = T(2 * r + 1, 2 * p + 1);
+    }
+  for (int j = 0; j < dp; ++j) rec[nt + j] = (j < d) ? center[j] : 0.0;
+  for (int s = 0; s < kNumScalars; ++s) rec[nt + dp + s] = scalars[s];
+  return 0;
+}
+
+static int eval_validate(int64_t n, int64_t ldx, int d, int kl, int k_out, int mode, const void* lp, const void* resp,
+                         const void* aux) {
+  PMC_REQUIRE(d >= 1 && d <= PMCB200_MAX_DIM, "mixture_eval: dimension must be in 1..64");
+  PMC_REQUIRE(n >= 0 && ldx >= d, "mixture_eval: bad n / ldx");
+  PMC_REQUIRE(kl >= 1, "mixture_eval: at least one component must be evaluated");
+  PMC_REQUIRE(mode >= 0 && mode <= 2, "mixture_eval: unknown mode");
+  PMC_REQUIRE((!lp && !resp && !aux) || k_out >= 1, "mixture_eval: k_out must be >= 1 when N x K outputs are requested");
+  return 0;
+}
+
+static int eval_launch(pmcb200_ctx* c, DevBuf& ws, const EvalArgs& a0, double* sums_dev, cudaStream_t st) {
+  EvalArgs a = a0;
+  const int dp = (a.d + 1) & ~1;
+  const int ts = k1_tile_rows(dp), nw = k1_warps(dp);
+  const int64_t tiles = (a.n + ts - 1) / ts;
+  const int grid = int(std::min<int64_t>(tiles, c->sm_count));
+  a.partials = nullptr;
+  if (sums_dev) {
+    if (int rc = ensure(ws, size_t(grid) * nw * 2 * sizeof(double))) return rc;
+    a.partials = static_cast<double*>(ws.p);
+  }
+  const int e = k1_launch(dp, a, grid, st);
+  if (e != 0) {
+    set_last_error(std::string("k1_mixture_eval launch: ") + cudaGetErrorString(cudaError_t(e)));
+    return 1;
+  }
+  c->launches++;
+  if (sums_dev) {
+    k1_reduce_sums<<<1, 32, 0, st>>>(a.partials, grid * nw, sums_dev);
+    PMC_CUDA_CHECK(cudaGetLastError());
+    c->launches++;
+  }
+  return 0;
+}
+
+int pmcb200_mixture_eval(pmcb200_ctx* c, const double* x, int64_t n, int64_t ldx, int d, const double* records,
+                         const int* cols, int kl, int k_out, int mode, double max_init, double* logq, double* lp,
+                         double* resp, double* aux, const double* weights, double* sums, void* stream) {
+  PMC_REQUIRE(c != nullptr, "mixture_eval: NULL context");
+  if (int rc = eval_validate(n, ldx, d, kl, k_out, mode, lp, resp, aux)) return rc;
+  PMC_CUDA_CHECK(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n == 0) {
+    if (sums) PMC_CUDA_CHECK(cudaMemsetAsync(sums, 0, 2 * sizeof(double), st));
+    return 0;
+  }
+  PMC_REQUIRE(x && records && cols, "mixture_eval: NULL input");
+  EvalArgs a{x, n, ldx, d, records, cols, kl, k_out, mode, max_init, logq, lp, resp, aux, weights, nullptr};
+  return eval_launch(c, c->ws, a, sums, st);
+}
+
+int pmcb200_suffstats(pmcb200_ctx* c, const double* x, int64_t n, int64_t ldx, int d, const double* shift,
+                      const double* rho, const double* gamma, int k, int ld_rho, const double* weights, double* out,
+                      void* stream) {
+  PMC_REQUIRE(c != nullptr, "suffstats: NULL context");
+  PMC_REQUIRE(d >= 1 && d <= 181, "suffstats: dimension must be in 1..181");
+  PMC_REQUIRE(k >= 1 && ld_rho >= k && n >= 0 && ldx >= d, "suffstats: bad sizes");
+  PMC_REQUIRE(out != nullptr, "suffstats: NULL output");
+  PMC_CUDA_CHECK(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int F = 1 + d + d * (d + 1) / 2;
+  const int64_t len = int64_t(k) * (F + 2);
+  if (n == 0) {
+    PMC_CUDA_CHECK(cudaMemsetAsync(out, 0, len * sizeof(double), st));
+    return 0;
+  }
+  PMC_REQUIRE(x && shift && rho, "suffstats: NULL input");
+  StatsArgs a;
+  a.x = x; a.n = n; a.ldx = ldx; a.d = d; a.shift = shift; a.rho = rho; a.gamma = gamma; a.sw = weights;
+  a.k = k; a.ld_rho = ld_rho; a.F = F;
+  a.units_k = (k + K2_TK - 1) / K2_TK;
+  a.units_f = (F + K2_TF - 1) / K2_TF;
+  a.wk = std::min(a.units_k, K2_MAX_WARPS);
+  a.wf = std::max(1, std::min(a.units_f, K2_MAX_WARPS / a.wk));
+  const int chunks_k = (a.units_k + a.wk - 1) / a.wk, chunks_f = (a.units_f + a.wf - 1) / a.wf;
+  const int KC = a.wk * K2_TK, FC = a.wf * K2_TF;
+  const size_t per_row = sizeof(double) * (size_t(d) + size_t(KC) * (gamma ? 3 : 1) + FC);
+  const size_t fixed = sizeof(short2) * FC + 64;
+  int tn = int((size_t(200) * 1024 - fixed) / per_row);
+  tn = std::max(2, std::min(64, tn)) & ~1;
+  a.tn = tn;
+  const size_t smem = per_row * tn + fixed + 16;
+  const int nwarps = a.wk * a.wf;
+  const int64_t tiles = (n + tn - 1) / tn;
+  const int ctas_target = c->sm_count * std::max(1, K2_MAX_WARPS / nwarps);
+  const int gy = chunks_k * chunks_f;
+  const int gx = int(std::max<int64_t>(1, std::min<int64_t>(tiles, ctas_target / gy)));
+  if (int rc = ensure(c->ws, size_t(gx) * len * sizeof(double))) return rc;
+  a.partial = static_cast<double*>(c->ws.p);
+  static bool attr_set = false;
+  if (!attr_set) {
+    PMC_CUDA_CHECK(cudaFuncSetAttribute(k2_suffstats, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  k2_suffstats<<<dim3(gx, gy), nwarps * 32, smem, st>>>(a);
+  PMC_CUDA_CHECK(cudaGetLastError());
+  k2_reduce_partials<<<unsigned((len + 255) / 256), 256, 0, st>>>(a.partial, gx, len, out);
+  PMC_CUDA_CHECK(cudaGetLastError());
+  c->launches += 2;
+  return 0;
+}
+
+int pmcb200_mixture_eval_host(pmcb200_ctx* c, const double* x, int64_t n, int64_t ldx, int d, const double* records,
+                              const int* cols, int kl, int k_out, int mode, double max_init, double* logq, double* lp,
+                              double* resp, double* aux, const double* weights, double* sums, int64_t chunk_rows) {
+  PMC_REQUIRE(c != nullptr, "mixture_eval_host: NULL context");
+  if (int rc = eval_validate(n, ldx, d, kl, k_out, mode, lp, resp, aux)) return rc;
+  PMC_CUDA_CHECK(cudaSetDevice(c->device));
+  if (sums) sums[0] = sums[1] = 0.0;
+  if (n == 0) return 0;
+  PMC_REQUIRE(x && records && cols, "mixture_eval_host: NULL input");
+  const int dp = (d + 1) & ~1;
+  const int rl = record_len(dp);
+  if (chunk_rows <= 0) chunk_rows = int64_t(1) << 18;
+  chunk_rows = std::min(chunk_rows, n);
+  const bool need_scratch = (resp != nullptr) || (mode == MODE_VB && lp != nullptr);
+
+  if (int rc = ensure(c->hrec, size_t(kl) * rl * sizeof(double))) return rc;
+  if (int rc = ensure(c->hcols, size_t(kl) * sizeof(int))) return rc;
+  PMC_CUDA_CHECK(cudaMemcpyAsync(c->hrec.p, records, size_t(kl) * rl * sizeof(double), cudaMemcpyHostToDevice, c->copy_stream[0]));
+  PMC_CUDA_CHECK(cudaMemcpyAsync(c->hcols.p, cols, size_t(kl) * sizeof(int), cudaMemcpyHostToDevice, c->copy_stream[0]));
+  PMC_CUDA_CHECK(cudaStreamSynchronize(c->copy_stream[0]));
+
+  const size_t nk_bytes = size_t(chunk_rows) * std::max(k_out, 1) * sizeof(double);
+  for (int s = 0; s < 2; ++s) {
+    if (int rc = ensure(c->hx[s], size_t(chunk_rows) * d * sizeof(double))) return rc;
+    if (weights)
+      if (int rc = ensure(c->hw[s], size_t(chunk_rows) * sizeof(double))) return rc;
+    if (int rc = ensure(c->hlogq[s], size_t(chunk_rows) * sizeof(double))) return rc;
+    if (lp || (need_scratch && !resp))
+      if (int rc = ensure(c->hlp[s], nk_bytes)) return rc;
+    if (resp)
+      if (int rc = ensure(c->hresp[s], nk_bytes)) return rc;
+    if (aux)
+      if (int rc = ensure(c->haux[s], nk_bytes)) return rc;
+    if (int rc = ensure(c->hsums[s], 2 * sizeof(double))) return rc;
+  }
+
+  const int64_t nchunks = (n + chunk_rows - 1) / chunk_rows;
+  std::vector<double> chunk_sums(size_t(nchunks) * 2, 0.0);
+  for (int64_t ci = 0; ci < nchunks; ++ci) {
+    const int s = int(ci & 1);
+    cudaStream_t st = c->copy_stream[s];
+    const int64_t r0 = ci * chunk_rows, rows = std::min(chunk_rows, n - r0);
+    // the slot's previous chunk (ci-2) was queued on the same stream, so stream order protects the buffers
+    if (ldx == d) {
+      PMC_CUDA_CHECK(cudaMemcpyAsync(c->hx[s].p, x + r0 * ldx, size_t(rows) * d * sizeof(double), cudaMemcpyHostToDevice, st));
+    } else {
+      PMC_CUDA_CHECK(cudaMemcpy2DAsync(c->hx[s].p, size_t(d) * sizeof(double), x + r0 * ldx, size_t(ldx) * sizeof(double),
+                                       size_t(d) * sizeof(double), size_t(rows), cudaMemcpyHostToDevice, st));
+    }
+    if (weights)
+      PMC_CUDA_CHECK(cudaMemcpyAsync(c->hw[s].p, weights + r0, size_t(rows) * sizeof(double), cudaMemcpyHostToDevice, st));
+    EvalArgs a{static_cast<const double*>(c->hx[s].p), rows, d, d,
+               static_cast<const double*>(c->hrec.p), static_cast<const int*>(c->hcols.p), kl, k_out, mode, max_init,
+               static_cast<double*>(c->hlogq[s].p),
+               lp ? static_cast<double*>(c->hlp[s].p) : nullptr,
+               resp ? static_cast<double*>(c->hresp[s].p) : nullptr,
+               aux ? static_cast<double*>(c->haux[s].p) : nullptr,
+               weights ? static_cast<const double*>(c->hw[s].p) : nullptr, nullptr};
+    if (int rc = eval_launch(c, c->hws[s], a, sums ? static_cast<double*>(c->hsums[s].p) : nullptr, st)) return rc;
+    if (logq) PMC_CUDA_CHECK(cudaMemcpyAsync(logq + r0, c->hlogq[s].p, size_t(rows) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    const size_t out_bytes = size_t(rows) * k_out * sizeof(double);
+    if (lp) PMC_CUDA_CHECK(cudaMemcpyAsync(lp + r0 * k_out, c->hlp[s].p, out_bytes, cudaMemcpyDeviceToHost, st));
+    if (resp) PMC_CUDA_CHECK(cudaMemcpyAsync(resp + r0 * k_out, c->hresp[s].p, out_bytes, cudaMemcpyDeviceToHost, st));
+    if (aux) PMC_CUDA_CHECK(cudaMemcpyAsync(aux + r0 * k_out, c->haux[s].p, out_bytes, cudaMemcpyDeviceToHost, st));
+    if (sums)
+      PMC_CUDA_CHECK(cudaMemcpyAsync(&chunk_sums[size_t(ci) * 2], c->hsums[s].p, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  }
+  PMC_CUDA_CHECK(cudaStreamSynchronize(c->copy_stream[0]));
+  PMC_CUDA_CHECK(cudaStreamSynchronize(c->copy_stream[1]));
+  if (sums)
+    for (int64_t ci = 0; ci < nchunks; ++ci) {
+      sums[0] += chunk_sums[size_t(ci) * 2];
+      sums[1] += chunk_sums[size_t(ci) * 2 + 1];
+    }
+  return 0;
+}
+
+int pmcb200_fp64_peak(pmcb200_ctx* c, int which, int iters, double* gflops_out, double* ms_out) {
+  PMC_REQUIRE(c != nullptr, "fp64_peak: NULL context");
+  PMC_REQUIRE(which >= 0 && which <= 3 && iters > 0, "fp64_peak: bad arguments");
+  PMC_CUDA_CHECK(cudaSetDevice(c->device));
+  if (int rc = ensure(c->ws, 64)) return rc;
+  double* out = static_cast<double*>(c->ws.p);
+  const int grid = c->sm_count * 2;
+  cudaEvent_t e0, e1;
+  PMC_CUDA_CHECK(cudaEventCreate(&e0));
+  PMC_CUDA_CHECK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep) {  // rep 0 warms up
+    PMC_CUDA_CHECK(cudaEventRecord(e0, 0));
+    switch (which) {
+      case 0: mb_dfma<0><<<grid, MB_THREADS>>>(iters, 1.0, out); break;
+      case 1: mb_dfma<1><<<grid, MB_THREADS>>>(iters, 1.0, out); break;
+      case 2: mb_dfma<2><<<grid, MB_THREADS>>>(iters, 1.0, out); break;
+      default: mb_dmma<<<grid, MB_THREADS>>>(iters, 1.0, out); break;
+    }
+    PMC_CUDA_CHECK(cudaGetLastError());
+    PMC_CUDA_CHECK(cudaEventRecord(e1, 0));
+    PMC_CUDA_CHECK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    PMC_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0) best = std::min(best, ms);
+    c->launches++;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  // flops: FMA = 2 flop.  DFMA kernels: 64 FMA / thread / iter.  DMMA: 64 mma / warp / iter, 8*8*4 FMA each.
+  const double threads = double(grid) * MB_THREADS;
+  const double fma = (which == 3) ? (threads / 32.0) * 64.0 * 256.0 * iters : threads * 64.0 * iters;
+  if (gflops_out) *gflops_out = 2.0 * fma / (best * 1e-3) * 1e-9;
+  if (ms_out) *ms_out = best;
+  return 0;
+}
+
+int64_t pmcb200_launch_count(pmcb200_ctx* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,187 @@
+"""Mixture densities with the API of pypmc/density/mixture.pyx (``MixtureDensity`` :21-212 and the
+create/recover helpers :214-350).  ``multi_evaluate`` is one launch of the fused CUDA kernel K1."""
+import numpy as _np
+from copy import deepcopy as _deepcopy
+
+from .base import ProbabilityDensity
+from .gauss import Gauss
+from .student_t import StudentT
+from ._eval import run_k1
+from .. import _lib
+from .. import _device as _dev
+
+
+class MixtureDensity(ProbabilityDensity):
+    """Weighted sum of component densities (mixture.pyx:21-212).
+
+    :param components: iterable of densities (deep-copied).
+    :param weights: iterable of floats, normalised on construction; equal weights if omitted.
+    """
+
+    def __init__(self, components, weights=None):
+        self.components = [_deepcopy(c) for c in components]
+        assert self.components, "Must have at least one component!"
+        self.dim = self.components[0].dim
+        _np.testing.assert_equal([c.dim for c in self.components], [self.dim] * len(self.components))
+        if weights is None:
+            self.weights = _np.ones(len(self.components))
+        else:
+            self.weights = _np.array(weights, dtype=float)
+            assert len(self.weights) == len(self.components)
+        self.normalize()
+
+    def __len__(self):
+        k = len(self.components)
+        assert k == len(self.weights)
+        return k
+
+    def normalize(self):
+        """Scale the component weights to sum to one."""
+        self.weights /= self.weights.sum()
+
+    def normalized(self):
+        """True if the component weights sum to one (within ``allclose``)."""
+        return bool(_np.allclose(self.weights.sum(), 1.0))
+
+    def prune(self, threshold=0.0):
+        """Remove components with weight <= ``threshold``; return ``[(index, component, weight), ...]``
+        in descending index order (mixture.pyx:64-94)."""
+        removed = []
+        for idx in range(len(self.weights) - 1, -1, -1):
+            if self.weights[idx] <= threshold:
+                removed.append((idx, self.components.pop(idx), self.weights[idx]))
+        self.weights = _np.delete(self.weights, [r[0] for r in removed])
+        return removed
+
+    # -- CUDA path ------------------------------------------------------------------------------------------
+    def _kernel_mode(self):
+        """K1 mode if every component is a ``Gauss`` or every component is a ``StudentT``; else None."""
+        if all(type(c) is Gauss or isinstance(c, Gauss) for c in self.components):
+            return _lib.MODE_GAUSS
+        if all(isinstance(c, StudentT) for c in self.components):
+            return _lib.MODE_STUDENT_T
+        return None
+
+    def _require_mode(self):
+        mode = self._kernel_mode()
+        if mode is None:
+            raise NotImplementedError(
+                "pypmc_b200 evaluates mixtures whose components are all Gauss or all StudentT on the GPU; "
+                "other component types are outside the accelerated path and there is no CPU fallback")
+        if self.dim > _lib.MAX_DIM:
+            raise NotImplementedError("dimension %d exceeds the CUDA kernels' maximum of %d" % (self.dim, _lib.MAX_DIM))
+        return mode
+
+    def _packed(self, components=None, compact=False):
+        """Packed records of ``components`` (default all); ``compact`` numbers the output columns 0..len-1."""
+        ks = list(range(len(self))) if components is None else [int(k) for k in components]
+        recs = _np.stack([self.components[k]._packed_record() for k in ks])
+        cols = list(range(len(ks))) if compact else ks
+        return _dev.PackedComponents(recs, cols, weights=self.weights[ks])
+
+    def evaluate(self, x, individual=False):
+        """log q(x) for one point (mixture.pyx:101-110); with ``individual`` also the component log-pdfs."""
+        x = _np.ascontiguousarray(x, dtype=float).reshape(1, -1)
+        ind = _np.empty((1, len(self)))
+        res = float(self.multi_evaluate(x, individual=ind)[0])
+        return (res, ind[0]) if individual else res
+
+    def multi_evaluate(self, x, out=None, individual=None, components=None):
+        """Evaluate the mixture at every row of ``x`` (mixture.pyx:112-156).
+
+        Returns log q(x_n) (in ``out`` if given) unless ``components`` is given, in which case only the
+        columns ``individual[:, k]``, k in ``components``, are filled and None is returned.  ``x`` may be
+        a float64 numpy array (streamed through the GPU) or a float64 torch CUDA tensor (device resident;
+        outputs are CUDA tensors).  Assumes normalised weights.
+        """
+        x = _dev.as_samples(x)
+        n, k = x.shape[0], len(self)
+        assert x.shape[1] == self.dim, "The points in ``x`` have the wrong dimension (%i instead of %i)" % (x.shape[1], self.dim)
+        if individual is not None:
+            assert len(x) == len(individual), "For the provided ``x``, ``individual`` must have shape %s" % ((n, k),)
+            assert individual.shape[1] == k, "For the provided ``x``, ``individual`` must have shape %s" % ((n, k),)
+        mode = self._require_mode()
+        assert (self.weights >= 0.0).all(), "Found negative weight"
+        on_device = _dev.is_device_tensor(x)
+        t = _dev.torch() if on_device else None
+
+        if components is not None:
+            assert out is None, 'If ``components`` is not None, ``out`` must be None.'
+            comps = [int(c) for c in components]
+            if not comps:
+                return None
+            if on_device:
+                if individual is None:
+                    individual = t.empty((n, k), dtype=t.float64, device=x.device)
+                run_k1(x, self._packed(comps), k, mode, lp=individual)
+            else:
+                if individual is None:
+                    individual = _np.empty((n, k))
+                tmp = _np.empty((n, len(comps)))
+                run_k1(x, self._packed(comps, compact=True), len(comps), mode, lp=tmp)
+                individual[:, comps] = tmp
+            return None
+
+        if out is not None:
+            assert len(out) == len(x), '``out`` must have length %i' % (len(x))
+        if on_device:
+            res = out if out is not None else t.empty(n, dtype=t.float64, device=x.device)
+            run_k1(x, self._packed(), k, mode, logq=res, lp=individual)
+            return res
+        direct_out = out is None or (isinstance(out, _np.ndarray) and out.dtype == _np.float64
+                                     and out.flags.c_contiguous and out.ndim == 1)
+        res = (out if out is not None else _np.empty(n)) if direct_out else _np.empty(n)
+        direct_ind = individual is None or (individual.dtype == _np.float64 and individual.flags.c_contiguous)
+        ind = individual if direct_ind else _np.empty((n, k))
+        run_k1(x, self._packed(), k, mode, logq=res, lp=ind)
+        if not direct_ind:
+            individual[:] = ind
+        if not direct_out:
+            out[:] = res
+            return out
+        return res
+
+    def propose(self, N=1, rng=_np.random.mtrand, trace=False, shuffle=True):
+        """Draw ``N`` points (mixture.pyx:159-212): multinomial counts per component, component draws in
+        component order, then either the origin array (``trace``) or an in-place shuffle (``shuffle``)."""
+        if trace and shuffle:
+            raise ValueError('Either ``shuffle`` or ``trace`` must be ``False``!')
+        counts = rng.multinomial(N, self.weights)
+        samples = _np.empty((N, self.dim))
+        start = 0
+        for comp, cnt in zip(self.components, counts):
+            if cnt != 0:
+                samples[start:start + cnt] = comp.propose(cnt)
+            start += cnt
+        if trace:
+            return samples, _np.repeat(_np.arange(len(self.components)), counts)
+        if shuffle:
+            rng.shuffle(samples)
+        return samples
+
+
+def create_gaussian_mixture(means, covs, weights=None):
+    """:class:`MixtureDensity` of :class:`Gauss` components (mixture.pyx:214-246)."""
+    assert len(means) == len(covs), \
+        'Number of means (%i) does not match number of covariances (%i)' % (len(means), len(covs))
+    return MixtureDensity([Gauss(m, c) for m, c in zip(means, covs)], weights)
+
+
+def recover_gaussian_mixture(mixture):
+    """``(means, covs, weights)`` of a Gaussian mixture (mixture.pyx:248-278)."""
+    means = _np.array([c.mu for c in mixture.components]).reshape(len(mixture.components), mixture.dim)
+    covs = _np.array([c.sigma for c in mixture.components]).reshape(len(means), mixture.dim, mixture.dim)
+    return means, covs, _np.array(mixture.weights)
+
+
+def create_t_mixture(means, covs, dofs, weights=None):
+    """:class:`MixtureDensity` of :class:`StudentT` components (mixture.pyx:280-318)."""
+    assert (len(means) == len(covs)) and (len(means) == len(dofs)), \
+        'Number of ``means`` (%i), ``covs`` (%i) and ``dofs`` (%i) do not match.' % (len(means), len(covs), len(dofs))
+    return MixtureDensity([StudentT(m, c, d) for m, c, d in zip(means, covs, dofs)], weights)
+
+
+def recover_t_mixture(mixture):
+    """``(means, covs, dofs, weights)`` of a Student-t mixture (mixture.pyx:320-350)."""
+    means, covs, weights = recover_gaussian_mixture(mixture)
+    return means, covs, _np.array([c.dof for c in mixture.components], dtype=float), weights

@@ -1,0 +1,354 @@
+"""Population Monte Carlo proposal updates with the API of pypmc/mix_adapt/pmc.pyx:
+``gaussian_pmc`` (:120-246), ``student_t_pmc`` (:499-739) and the ``PMC`` driver (:248-476).
+
+Per update: ONE launch of kernel K1 (log-pdfs, log-sum-exp, rho_nk [, gamma_nk], sum_n w_n log q_n) and ONE
+launch of kernel K2 (A_k, B_k, first and second moments, dof statistic), one all-reduce of the K-row packet
+when samples are sharded over GPUs (``pypmc_b200.parallel``), then K-sized host arithmetic and the same
+per-component ``update`` / ``LinAlgError`` handling as the reference.  Samples, rho and gamma stay on the
+device; ``PMC`` uploads the samples once for all its EM steps (pmc.pyx:362,447 keeps them fixed).
+"""
+from __future__ import division
+
+import logging
+from copy import deepcopy as _cp
+
+import numpy as _np
+from scipy.optimize import brentq as _find_root
+from scipy.special import digamma as _psi
+
+from ..density.gauss import Gauss
+from ..density.mixture import MixtureDensity
+from ..density.student_t import StudentT
+from ..density._eval import run_k1
+from .. import _device as _dev
+from .. import _lib
+from .. import parallel as _parallel
+from ._stats import PacketLayout, moments_from_stats
+
+logger = logging.getLogger(__name__)
+
+
+class DeviceSamples(object):
+    """This rank's (samples, importance weights, latent indices), resident on the GPU."""
+
+    def __init__(self, samples, weights=None, latent=None):
+        x = _dev.as_samples(samples)
+        self.N, self.D = int(x.shape[0]), int(x.shape[1])
+        self.x = _dev.to_device(x).contiguous()
+        self.w = None if weights is None else _dev.to_device(_np.asarray(weights, dtype=_np.float64)
+                                                              if not _dev.is_device_tensor(weights) else weights)
+        if latent is None:
+            self.latent = None
+        else:
+            t = _dev.torch()
+            self.latent = latent.to(t.int64) if _dev.is_device_tensor(latent) else _dev.to_device(_np.asarray(latent, dtype=_np.int64))
+        self.rho = None      # [N, K] responsibilities of the last E-pass (device)
+        self.gamma = None    # [N, K] Student-t gamma of the last E-pass (device)
+
+
+def _check_arguments(samples, weights, latent, mincount, rb):
+    """Argument contradictions, same messages as pmc.pyx:70-83."""
+    if weights is not None and not isinstance(samples, DeviceSamples):
+        shape = tuple(weights.shape) if hasattr(weights, "shape") else _np.asarray(weights).shape
+        assert len(shape) == 1, 'Weights must be one-dimensional.'
+        assert shape[0] == len(samples), \
+            "Number of weights (%s) does not match the number of samples (%s)." % (shape[0], len(samples))
+    if latent is None:
+        if mincount > 0:
+            raise ValueError('`mincount` must be 0 if `latent` is not provided!')
+        if not rb:
+            raise ValueError('`rb` must be True if `latent` is not provided!')
+
+
+def _mixture_shift(density, live):
+    """Shift vector for K2's raw moments: the weight-averaged centre of the live components."""
+    w = _np.array([density.weights[k] for k in live], dtype=float)
+    mus = _np.array([density.components[k].mu for k in live], dtype=float)
+    if not _np.isfinite(w).all() or w.sum() <= 0:
+        return mus.mean(axis=0)
+    return (w[:, None] * mus).sum(axis=0) / w.sum()
+
+
+def _e_pass_and_stats(ds, density, live, rb, mode):
+    """K1 + K2 on this rank's samples, all-reduce, return (layout, unpacked statistics, shift)."""
+    t = _dev.torch()
+    K, D, N = len(density), density.dim, ds.N
+    assert ds.D == D, "The points in ``x`` have the wrong dimension (%i instead of %i)" % (ds.D, D)
+    lay = PacketLayout(K, D)
+    device = ds.x.device
+    packet = t.zeros(lay.size, dtype=t.float64, device=device)
+    student = (mode == _lib.MODE_STUDENT_T)
+    alloc = t.empty if len(live) == K else t.zeros       # dead columns must read 0 (pmc.pyx:26)
+    sums = packet[lay.off_sum_a:lay.off_sum_a + 2]
+    packed = density._packed(live) if live else None
+
+    if ds.rho is None or tuple(ds.rho.shape) != (N, K) or len(live) != K:
+        ds.rho = alloc((N, K), dtype=t.float64, device=device)
+    if student and (ds.gamma is None or tuple(ds.gamma.shape) != (N, K) or len(live) != K):
+        ds.gamma = alloc((N, K), dtype=t.float64, device=device)
+    gamma = ds.gamma if student else None
+
+    if live:
+        if rb:
+            run_k1(ds.x, packed, K, mode, resp=ds.rho, aux=gamma, weights=ds.w, sums=sums)
+        else:
+            # latent variables known: one-hot responsibilities (pmc.pyx:45-51); K1 only for gamma / sums
+            ds.rho.zero_()
+            live_mask = t.zeros(K + 1, dtype=t.bool, device=device)
+            live_mask[t.tensor(live, device=device)] = True
+            lat = ds.latent.clamp(min=-1, max=K)
+            ok = (lat >= 0) & (lat < K) & live_mask[lat.clamp(min=0)]
+            rows = t.nonzero(ok, as_tuple=True)[0]
+            ds.rho[rows, lat[rows]] = 1.0
+            if student:
+                run_k1(ds.x, packed, K, mode, aux=gamma, weights=ds.w, sums=sums)
+            else:
+                sums[1] = float(N) if ds.w is None else ds.w.sum()
+    if ds.latent is not None:
+        lat = ds.latent
+        inside = (lat >= 0) & (lat < K)
+        packet[lay.off_counts:lay.off_counts + K] = t.bincount(lat[inside], minlength=K)[:K].to(t.float64)
+
+    shift = _mixture_shift(density, live) if live else _np.zeros(D)
+    _lib.Context.get().suffstats(ds.x, N, ds.x.stride(0) if N > 1 else D, D, _dev.to_device(shift), ds.rho, gamma, K, K,
+                                 ds.w, packet, _dev.current_stream_ptr())
+    _parallel.allreduce_(packet)
+    return lay, lay.unpack(packet.cpu().numpy()), shift
+
+
+def _live_components(density):
+    return [k for k in range(len(density)) if density.weights[k] != 0]
+
+
+def _kill_undersampled(density, live, counts, mincount):
+    """Components that proposed fewer than ``mincount`` samples die AFTER rho was computed (pmc.pyx:109-116).
+    The reference removes from the list it is iterating, so the element following a removed one is not
+    examined; the index arithmetic below reproduces exactly that traversal."""
+    died = False
+    i = 0
+    while i < len(live):
+        k = live[i]
+        if counts[k] < mincount:
+            live.pop(i)
+            density.weights[k] = 0.
+            died = True
+            logger.warning("Component %i died because of too few (%i) samples." % (k, counts[k]))
+        i += 1
+    return died
+
+
+def _apply_update(density, live, alpha, mean, cov, new_dof=None):
+    """Install the new parameters; a component whose covariance is not positive definite keeps its old
+    parameters and gets weight zero (pmc.pyx:227-244, :713-737).  Returns True if that happened."""
+    failed = False
+    for k in live:
+        comp = density.components[k]
+        density.weights[k] = alpha[k]
+        old = (comp.mu, comp.sigma) if new_dof is None else (comp.mu, comp.sigma, comp.dof)
+        try:
+            if new_dof is None:
+                comp.update(mean[k], cov[k])
+            else:
+                comp.update(mean[k], cov[k], new_dof[k])
+        except _np.linalg.LinAlgError:
+            logger.warning("Could not update component %i --> weight is set to zero." % k)
+            comp.update(*old)
+            density.weights[k] = 0.
+            failed = True
+    return failed
+
+
+def _as_device_samples(samples, weights, latent):
+    if isinstance(samples, DeviceSamples):
+        return samples
+    return DeviceSamples(samples, weights, latent)
+
+
+def _pmc_update(samples, density, weights, latent, rb, mincount, copy, mode, dof_args=None):
+    _check_arguments(samples, weights, latent, mincount, rb)
+    if copy:
+        density = _cp(density)
+    ds = _as_device_samples(samples, weights, latent)
+    if not isinstance(density, MixtureDensity) or density._require_mode() != mode:
+        raise TypeError("``density`` must be a MixtureDensity with %s components"
+                        % ("StudentT" if mode == _lib.MODE_STUDENT_T else "Gauss"))
+    live = _live_components(density)
+    old_dofs = [c.dof for c in density.components] if mode == _lib.MODE_STUDENT_T else None
+
+    lay, st, shift = _e_pass_and_stats(ds, density, live, rb, mode)
+    need_renormalize = False
+    if ds.latent is not None:
+        need_renormalize = _kill_undersampled(density, live, st["counts"], mincount)
+
+    weight_normalization = st["sumw"]
+    A_reg, mean, cov = moments_from_stats(st, shift, "B")
+    alpha = A_reg / weight_normalization                       # pmc.pyx:191-193
+
+    new_dof = None
+    if mode == _lib.MODE_STUDENT_T:
+        new_dof = _solve_dofs(density, live, st, old_dofs, weight_normalization, **dof_args)
+
+    if _apply_update(density, live, alpha, mean, cov, new_dof):
+        need_renormalize = True
+    if need_renormalize:
+        density.normalize()
+    density._last_sums = (st["sum_a"], st["sumw"])             # sum_n w_n log q_old(x_n), sum_n w_n
+    return density
+
+
+def gaussian_pmc(samples, density, weights=None, latent=None, rb=True, mincount=0, copy=True):
+    """Adapt a Gaussian mixture with the (M-)PMC update [Cap+08, Kil+09]; API of pmc.pyx:120-246.
+
+    :param samples: (N x D) float64 numpy array or torch CUDA tensor -- this rank's samples.
+    :param density: :class:`MixtureDensity` of :class:`Gauss` components that proposed them.
+    :param weights: N importance weights (unnormalised) or None for equal weights.
+    :param latent: N component indices that generated the samples, optional.
+    :param rb: Rao-Blackwellised responsibilities (True) or one-hot from ``latent`` (False).
+    :param mincount: components with fewer proposed samples are switched off (needs ``latent``).
+    :param copy: leave ``density`` untouched and return an updated copy (default) or update in place.
+    """
+    if samples is None:
+        raise TypeError("Argument 'samples' must not be None")
+    return _pmc_update(samples, density, weights, latent, rb, mincount, copy, _lib.MODE_GAUSS)
+
+
+class _DOFCondition(object):
+    """First-order condition for a Student-t component's degree of freedom, eq. (16) of [HOD12]
+    (pmc.pyx:478-497): root of const + ln(nu/2) - psi(nu/2)."""
+
+    def __init__(self, const):
+        self.const = float(const)
+
+    def __call__(self, nu):
+        return self.const + _np.log(.5 * nu) - _psi(.5 * nu)
+
+
+def _solve_dofs(density, live, st, old_dofs, weight_normalization, dof_solver_steps, mindof, maxdof):
+    K, D = len(density), density.dim
+    if not dof_solver_steps:
+        return list(old_dofs)
+    new_dof = [-1 for _ in range(K)]
+    W = st["sumw"]
+    for k in live:
+        nu = old_dofs[k]
+        A, B, L = st["A"][k], st["B"][k], st["L"][k]
+        # sum_n w (xi + delta), pmc.pyx:659-679, with ln((q+nu)/2) = ln((nu+D)/2) - ln(gamma)
+        total = (A * _np.log(.5 * (nu + D)) - L) - _psi(.5 * (D + nu)) * A \
+            + (W - A) * (_np.log(.5 * nu) - _psi(.5 * nu)) + B + (W - A)
+        condition = _DOFCondition(1. - total / weight_normalization)
+        try:
+            new_dof[k] = _find_root(condition, mindof, maxdof, maxiter=dof_solver_steps)
+        except RuntimeError:   # not converged
+            logger.warning("``dof`` solver for component %i did not converge." % k)
+            new_dof[k] = old_dofs[k]
+        except ValueError as error:
+            # same sign at both ends; the condition is decreasing in nu (pmc.pyx:700-710)
+            if condition(mindof) < 0.:
+                new_dof[k] = mindof
+            elif condition(maxdof) > 0.:
+                new_dof[k] = maxdof
+            else:
+                raise RuntimeError('``dof`` adaptation for component %i raised an error.' % k, error)
+    return new_dof
+
+
+def student_t_pmc(samples, density, weights=None, latent=None, rb=True, dof_solver_steps=100, mindof=1e-5,
+                  maxdof=1e3, mincount=0, copy=True):
+    """Adapt a Student-t mixture with the PMC update of [Cap+08] and the dof update of [HOD12]; API of
+    pmc.pyx:499-739.  Parameters as :func:`gaussian_pmc`, plus ``dof_solver_steps`` (0 = keep the degrees of
+    freedom), ``mindof`` and ``maxdof`` bracketing the root search."""
+    if samples is None:
+        raise TypeError("Argument 'samples' must not be None")
+    return _pmc_update(samples, density, weights, latent, rb, mincount, copy, _lib.MODE_STUDENT_T,
+                       dict(dof_solver_steps=dof_solver_steps, mindof=mindof, maxdof=maxdof))
+
+
+class PMC(object):
+    """Run several PMC updates on a fixed set of samples; API of pmc.pyx:248-476.
+
+    ``samples``, ``weights`` and ``latent`` are uploaded to the GPU once (they are not re-read afterwards);
+    ``density`` is always copied.  Additional keyword arguments go to the update function.
+    """
+
+    def __init__(self, samples, density, weights=None, latent=None, rb=True, mincount=0, **kwargs):
+        if samples is None:
+            raise TypeError("Argument 'samples' must not be None")
+        if weights is not None:
+            self.weights = weights if _dev.is_device_tensor(weights) else _np.asarray(weights)
+            assert len(self.weights.shape) == 1, 'Weights must be one-dimensional.'
+            assert len(self.weights) == len(samples), \
+                "Number of weights (%s) does not match the number of samples (%s)." % (len(self.weights), len(samples))
+        else:
+            self.weights = None
+        if latent is None:
+            if mincount > 0:
+                raise ValueError('`mincount` must be 0 if `latent` is not provided!')
+            if not rb:
+                raise ValueError('`rb` must be True if `latent` is not provided!')
+
+        error_wrong_mixture = '``density`` must be a ``pypmc.density.mixture.MixtureDensity`` with ' \
+            '``pypmc.density.gauss.Gauss`` or ``pypmc.density.student_t.StudentT`` components'
+        if not isinstance(density, MixtureDensity):
+            raise TypeError(error_wrong_mixture)
+        first = type(density.components[0])
+        if issubclass(first, Gauss):
+            self.pmc, kind = gaussian_pmc, Gauss
+        elif issubclass(first, StudentT):
+            self.pmc, kind = student_t_pmc, StudentT
+        else:
+            raise TypeError(error_wrong_mixture)
+        if not all(isinstance(c, kind) for c in density.components):
+            raise TypeError(error_wrong_mixture)
+
+        self.density = _cp(density)
+        self.samples = samples
+        self.latent = latent
+        self.rb = rb
+        self.mincount = mincount
+        self.additional_args = kwargs
+        self._device_samples = DeviceSamples(samples, weights, latent)
+
+    def log_likelihood(self):
+        """sum_n wbar_n log q(x_n), eq. (5) of [Cap+08] (pmc.pyx:371-391), over all ranks' samples."""
+        ds = self._device_samples
+        t = _dev.torch()
+        sums = t.zeros(2, dtype=t.float64, device=ds.x.device)
+        run_k1(ds.x, self.density._packed(), len(self.density), self.density._require_mode(), weights=ds.w, sums=sums)
+        _parallel.allreduce_(sums)
+        s = sums.cpu().numpy()
+        return float(s[0] / s[1])
+
+    def run(self, iterations=1000, prune=0., rel_tol=1e-10, abs_tol=1e-5, verbose=False):
+        """Iterate updates until the log-likelihood converges (pmc.pyx:393-476); returns the number of
+        iterations at convergence or None.  Convergence is never declared when the bound decreased."""
+        old_K = None
+        bound = None
+        for i in range(1, iterations + 1):
+            if old_K == len(self.density):
+                old_bound = bound
+            else:
+                old_bound = self.log_likelihood()
+                logger.info('New bound=%g, K=%i' % (old_bound, len(self.density)))
+
+            self.pmc(self._device_samples, self.density, self.weights, self.latent, self.rb, mincount=self.mincount,
+                     copy=False, **self.additional_args)
+            bound = self.log_likelihood()
+            logger.info('After update %d: bound=%.15g, K=%i, component_weights=%s'
+                        % (i, bound, len(self.density), self.density.weights))
+
+            if bound < old_bound:
+                logger.warning('Bound decreased from %g to %g' % (old_bound, bound))
+            if bound == old_bound:
+                return i
+            diff = bound - old_bound
+            if diff > 0:
+                if abs(bound) < abs_tol:
+                    if abs(diff) < abs_tol:
+                        return i
+                elif abs(diff / bound) < rel_tol:
+                    return i
+
+            old_K = len(self.density)
+            self.density.prune(prune)
+            self.density.normalize()
+        return None

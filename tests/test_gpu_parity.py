@@ -1,0 +1,343 @@
+"""Parity of the CUDA path (through the C ABI, via the pypmc-compatible classes) against
+
+(a) golden fixtures generated from the compiled, unmodified reference (tests/golden/*.npz),
+(b) the reference's own hand-computed golden numbers,
+(c) the CPU oracle on seeded inputs incl. edge cases (ragged N, odd D, dead components, strided views).
+
+Tolerance (BASELINE.json north_star): 1e-10 relative, float64.  Covariance-type outputs use the
+max-norm metric of SURVEY 8c (``mat_err``).  Needs a B200: ``pytest -m gpu``.
+"""
+import numpy as np
+import pytest
+
+from conftest import mat_err, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def pm():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import pypmc_b200
+    return pypmc_b200
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import oracle
+    return oracle
+
+
+def _mix(pm, g, t=False):
+    from pypmc_b200.density.mixture import create_gaussian_mixture, create_t_mixture
+    if t:
+        return create_t_mixture(g["means"], g["covs"], g["dofs"], g["weights"])
+    return create_gaussian_mixture(g["means"], g["covs"], g["weights"])
+
+
+# ------------------------------------------------------------------ (b) reference golden numbers
+def test_reference_golden_numbers(pm):
+    from pypmc_b200.density.gauss import Gauss
+    from pypmc_b200.density.student_t import StudentT
+    from pypmc_b200.density.mixture import MixtureDensity
+    # density/gauss_test.py:43-55, 111-160
+    g = Gauss([4.3, 1.1], [[0.01, 0.003], [0.003, 0.0025]])
+    assert g.evaluate(np.array([4.35, 1.2])) == pytest.approx(1.30077135, abs=1e-8)
+    out = np.empty(2)
+    res = g.multi_evaluate(np.array([[4.35, 1.2]] * 2), out)
+    assert res is out
+    np.testing.assert_allclose(out, 1.30077135, atol=1e-8)
+    # density/student_t_test.py:168-230, 155-166
+    t = StudentT([1.25, 4.3], [[0.0049, 0.0], [0.0, 0.01]], 5.0)
+    np.testing.assert_allclose(t.multi_evaluate(np.array([[1.3, 4.4], [1.26, 4.424]])), [2.200202941, 2.174596526], atol=1e-9)
+    cauchy = StudentT([0.0], [[1.0]], 1.0)
+    assert cauchy.evaluate(np.array([3.2])) == pytest.approx(-3.5642087303149452, abs=1e-12)
+    # density/mixture_test.py:29-33: two unit Gaussians in 1-d
+    mix = MixtureDensity([Gauss([0.0], [[1.0]]), Gauss([1.0], [[1.0]])], [0.4, 0.6])
+    x = np.array([[0.3]])
+    expect = np.log(0.4 * np.exp(-0.5 * 0.09) + 0.6 * np.exp(-0.5 * 0.49)) - 0.5 * np.log(2 * np.pi)
+    assert mix.multi_evaluate(x)[0] == pytest.approx(expect, rel=1e-14)
+    assert mix.evaluate(x[0]) == pytest.approx(expect, rel=1e-14)
+
+
+def test_gaussian_pmc_reference_tables(pm):
+    # mix_adapt/pmc_test.py:93-169 (hand-computed tables, assert_allclose default rtol 1e-7)
+    from test_oracle import PMC_MEANS, PMC_COVS, PMC_CW, PMC_SAMPLES, PMC_WEIGHTS
+    from pypmc_b200.density.mixture import create_gaussian_mixture
+    from pypmc_b200.mix_adapt.pmc import gaussian_pmc
+    prop = create_gaussian_mixture(PMC_MEANS, PMC_COVS, PMC_CW)
+    before = [c.mu.copy() for c in prop.components]
+    new = gaussian_pmc(PMC_SAMPLES, prop, PMC_WEIGHTS)
+    for c, b in zip(prop.components, before):      # copy=True leaves the input untouched (pmc_test.py:69-91)
+        np.testing.assert_array_equal(c.mu, b)
+    np.testing.assert_allclose(new.weights, np.array([154.54358983999998, 159.02061223999999]) / 313.56420207999997)
+    np.testing.assert_allclose(new.components[0].mu, np.array([1546.302278, -172.1300429, 1279.34733595]) / 154.54358983999998)
+    np.testing.assert_allclose(new.components[1].mu, np.array([-1652.19922509, 1150.52591727, 74.098254]) / 159.02061223999999)
+    np.testing.assert_allclose(new.components[0].sigma, np.array([[91.13245238, 62.95055712, 4.96175291],
+                                                                  [62.95055712, 51.04895641, -16.59026473],
+                                                                  [4.96175291, -16.59026473, 111.63047879]]) / 154.54358983999998)
+    new = gaussian_pmc(PMC_SAMPLES, prop)          # unweighted
+    np.testing.assert_allclose(new.weights, [0.6, 0.4])
+    np.testing.assert_allclose([c.mu for c in new.components],
+                               [[10.00569514, -1.11356905, 8.27908553], [-10.38983286, 7.23392486, 0.4632788]])
+    with pytest.raises(ValueError, match="mincount"):
+        gaussian_pmc(PMC_SAMPLES, prop, mincount=2)
+    with pytest.raises(ValueError, match="rb"):
+        gaussian_pmc(PMC_SAMPLES, prop, rb=False)
+
+
+# ------------------------------------------------------------------ (a) fixtures from the compiled reference
+@pytest.mark.parametrize("name", ["gauss_small", "gauss_c2", "gauss_c2_stress"])
+def test_gauss_mixture_fixture(pm, golden, name):
+    import torch
+    g = golden(name)
+    mix = _mix(pm, g)
+    x = g["x"]
+    n, k = len(x), len(mix)
+    ind = np.empty((n, k))
+    logq = mix.multi_evaluate(x, individual=ind)
+    rows = len(g["individual"])
+    assert rel_err(ind[:rows], g["individual"]) < TOL
+    assert rel_err(logq, g["logq"]) < TOL
+    # the same bits whichever of out / individual is passed (mixture_test.py:92-96)
+    out = np.empty(n)
+    assert mix.multi_evaluate(x, out) is out
+    np.testing.assert_array_equal(out, logq)
+    np.testing.assert_array_equal(mix.multi_evaluate(x), logq)
+    # device-resident samples give the same bits as streamed host samples
+    xd = torch.from_numpy(x).cuda()
+    indd = torch.empty((n, k), dtype=torch.float64, device="cuda")
+    lq = mix.multi_evaluate(xd, individual=indd)
+    np.testing.assert_array_equal(lq.cpu().numpy(), logq)
+    np.testing.assert_array_equal(indd.cpu().numpy(), ind)
+    # components subset only touches its columns (mixture.pyx:153-156)
+    ind2 = np.full((n, k), -7.0)
+    assert mix.multi_evaluate(x, individual=ind2, components=[1, k - 1]) is None
+    np.testing.assert_array_equal(ind2[:, [1, k - 1]], ind[:, [1, k - 1]])
+    assert (np.delete(ind2, [1, k - 1], axis=1) == -7.0).all()
+
+
+@pytest.mark.parametrize("name", ["gauss_small", "gauss_c2", "gauss_c2_stress"])
+def test_gaussian_pmc_fixture(pm, golden, name):
+    from pypmc_b200.mix_adapt.pmc import gaussian_pmc, PMC
+    g = golden(name)
+    mix = _mix(pm, g)
+    live = [k for k in range(len(mix)) if g["weights"][k] != 0]
+    variants = [("pmc_weighted", dict(weights=g["sample_weights"])), ("pmc_unweighted", dict())]
+    if "pmc_latent_rb_weights" in g:
+        variants += [("pmc_latent_rb", dict(weights=g["sample_weights"], latent=g["latent"], rb=True, mincount=2)),
+                     ("pmc_latent_nonrb", dict(weights=g["sample_weights"], latent=g["latent"], rb=False))]
+    for tag, kw in variants:
+        new = gaussian_pmc(g["x"], mix, **kw)
+        np.testing.assert_allclose(new.weights, g[tag + "_weights"], rtol=TOL, atol=1e-300)
+        mu = np.array([c.mu for c in new.components])
+        cov = np.array([c.sigma for c in new.components])
+        np.testing.assert_allclose(mu[live], g[tag + "_means"][live], rtol=TOL, atol=1e-12)
+        assert mat_err(cov[live], g[tag + "_covs"][live]) < TOL
+    p = PMC(g["x"], mix, weights=g["sample_weights"])
+    assert p.log_likelihood() == pytest.approx(float(g["loglik_weighted"]), rel=TOL)
+    assert PMC(g["x"], mix).log_likelihood() == pytest.approx(float(g["loglik_unweighted"]), rel=TOL)
+    if "pmc_run3_weights" in g:
+        conv = p.run(iterations=3)
+        assert (-1 if conv is None else conv) == int(g["pmc_run3_converged"])
+        np.testing.assert_allclose(p.density.weights, g["pmc_run3_weights"], rtol=1e-8)
+        assert mat_err(np.array([c.sigma for c in p.density.components]), g["pmc_run3_covs"]) < 1e-8
+        assert p.log_likelihood() == pytest.approx(float(g["pmc_run3_loglik"]), rel=1e-9)
+
+
+@pytest.mark.parametrize("name", ["student_small", "student_c4"])
+def test_student_fixture(pm, golden, name):
+    from pypmc_b200.mix_adapt.pmc import student_t_pmc
+    g = golden(name)
+    mix = _mix(pm, g, t=True)
+    x = g["x"]
+    ind = np.empty((len(x), len(mix)))
+    logq = mix.multi_evaluate(x, individual=ind)
+    rows = len(g["individual"])
+    assert rel_err(ind[:rows], g["individual"]) < TOL
+    assert rel_err(logq, g["logq"]) < TOL
+    variants = [("pmc_nodof_weighted", dict(weights=g["sample_weights"], dof_solver_steps=0)),
+                ("pmc_dof_weighted", dict(weights=g["sample_weights"]))]
+    if "pmc_dof_unweighted_weights" in g:
+        variants += [("pmc_nodof_unweighted", dict(dof_solver_steps=0)), ("pmc_dof_unweighted", dict()),
+                     ("pmc_dof_latent_nonrb", dict(weights=g["sample_weights"], latent=g["latent"], rb=False))]
+    for tag, kw in variants:
+        new = student_t_pmc(x, mix, **kw)
+        np.testing.assert_allclose(new.weights, g[tag + "_weights"], rtol=TOL)
+        np.testing.assert_allclose([c.mu for c in new.components], g[tag + "_means"], rtol=TOL, atol=1e-12)
+        assert mat_err(np.array([c.sigma for c in new.components]), g[tag + "_covs"]) < TOL
+        np.testing.assert_allclose([c.dof for c in new.components], g[tag + "_dofs"], rtol=1e-8)
+
+
+@pytest.mark.parametrize("name", ["vb_small", "vb_c3"])
+def test_vb_fixture(pm, golden, name):
+    from pypmc_b200.mix_adapt.variational import GaussianInference
+    from pypmc_b200.density.mixture import create_gaussian_mixture
+    g = golden(name)
+    mix = create_gaussian_mixture(g["means"], g["covs"], g["weights"])
+    tags = [("unw", None)] + ([("wgt", g["sample_weights"])] if "wgt_init_r" in g else [])
+    for tag, sw in tags:
+        vb = GaussianInference(g["x"], initial_guess=mix, weights=sw)
+
+        def check(stage):
+            p = lambda a: g["%s_%s_%s" % (tag, stage, a)]
+            rows = len(p("r"))
+            for a in ("alpha", "beta", "nu", "expectation_det_ln_lambda", "expectation_ln_pi", "N_comp"):
+                np.testing.assert_allclose(getattr(vb, a), p(a), rtol=TOL, err_msg=a)
+            np.testing.assert_allclose(vb.m, p("m"), rtol=TOL, atol=1e-12)
+            assert mat_err(vb.W, p("W")) < TOL
+            assert rel_err(vb.expectation_gauss_exponent[:rows], p("expectation_gauss_exponent")) < TOL
+            assert rel_err(vb.log_rho[:rows], p("log_rho")) < TOL
+            assert rel_err(vb.r[:rows], p("r")) < 1e-9       # exp() amplifies |log_rho| ~ 1e2..1e3 times eps
+            np.testing.assert_allclose(vb.x_mean_comp, p("x_mean_comp"), rtol=TOL, atol=1e-12)
+            assert mat_err(vb.S, p("S")) < TOL
+            np.testing.assert_allclose(vb.inv_N_comp, p("inv_N_comp"), rtol=TOL)
+
+        check("init")
+        assert vb.likelihood_bound() == pytest.approx(float(g[tag + "_init_bound"]), rel=TOL)
+        vb.update()
+        check("upd1")
+        assert vb.likelihood_bound() == pytest.approx(float(g[tag + "_upd1_bound"]), rel=TOL)
+        vb.update()
+        assert vb.likelihood_bound() == pytest.approx(float(g[tag + "_upd2_bound"]), rel=1e-9)
+        out = vb.make_mixture()
+        np.testing.assert_allclose(out.weights, g[tag + "_upd2_mix_weights"], rtol=1e-8)
+        assert mat_err(np.array([c.sigma for c in out.components]), g[tag + "_upd2_mix_covs"]) < 1e-8
+    if "first_run5_K" in g:
+        vb = GaussianInference(g["x"], components=len(mix) + 2)
+        assert vb.likelihood_bound() == pytest.approx(float(g["first_init_bound"]), rel=TOL)
+        it = vb.run(iterations=5, prune=1.0)
+        assert (-1 if it is None else it) == int(g["first_run5_converged"])
+        assert vb.K == int(g["first_run5_K"])
+        np.testing.assert_allclose(vb.N_comp, g["first_run5_N_comp"], rtol=1e-8)
+        assert vb.likelihood_bound() == pytest.approx(float(g["first_run5_bound"]), rel=1e-9)
+
+
+# ------------------------------------------------------------------ (c) oracle on seeded edge cases
+def _synth(K, D, N, seed, dof=None):
+    rng = np.random.default_rng(seed)
+    means = rng.normal(0.0, 3.0, size=(K, D))
+    covs = np.empty((K, D, D))
+    for k in range(K):
+        a = rng.normal(0.0, 1.0 / np.sqrt(D), size=(D, D))
+        covs[k] = a @ a.T + 0.5 * np.eye(D)
+    w = rng.uniform(0.5, 1.5, size=K)
+    comp = rng.integers(0, K, size=N)
+    x = means[comp] + np.einsum("nij,nj->ni", np.linalg.cholesky(covs)[comp], rng.normal(size=(N, D)))
+    if dof is not None:
+        x = means[comp] + (x - means[comp]) / np.sqrt(rng.chisquare(dof, size=N) / dof)[:, None]
+    return means, covs, w / w.sum(), np.ascontiguousarray(x), rng.uniform(0.5, 1.5, size=N)
+
+
+@pytest.mark.parametrize("K,D,N", [(1, 1, 1), (3, 2, 31), (2, 3, 33), (5, 7, 1537), (4, 13, 1000), (7, 20, 2049),
+                                   (3, 21, 777), (6, 33, 513), (2, 40, 300), (3, 41, 129), (2, 63, 200), (2, 64, 65)])
+def test_k1_vs_oracle_shapes(pm, orc, K, D, N):
+    from pypmc_b200.density.mixture import create_gaussian_mixture, create_t_mixture
+    means, covs, w, x, sw = _synth(K, D, N, seed=100 + D)
+    for dofs in (None, np.linspace(2.5, 9.0, K)):
+        comps = orc.Components(means, covs, dofs)
+        lq_ref, ind_ref = orc.mixture_multi_evaluate(x, comps, w)
+        mix = create_gaussian_mixture(means, covs, w) if dofs is None else create_t_mixture(means, covs, dofs, w)
+        ind = np.empty((N, K))
+        lq = mix.multi_evaluate(x, individual=ind)
+        assert rel_err(ind, ind_ref) < TOL
+        assert rel_err(lq, lq_ref) < TOL
+        # strided sample view (every other row, extra trailing columns)
+        big = np.zeros((2 * N, D + 3))
+        big[::2, :D] = x
+        assert rel_err(mix.multi_evaluate(big[::2, :D]), lq_ref) < TOL
+        # component-wise API
+        col = np.empty((N, K))
+        for k, c in enumerate(mix.components):
+            c.multi_evaluate(x, col[:, k])
+        np.testing.assert_array_equal(col, ind)
+
+
+def test_rho_gamma_vs_oracle_with_dead_components(pm, orc):
+    import torch
+    from pypmc_b200.density.mixture import create_t_mixture
+    from pypmc_b200.density._eval import run_k1
+    from pypmc_b200 import _lib
+    K, D, N = 6, 9, 1201
+    means, covs, w, x, sw = _synth(K, D, N, seed=7, dof=4.0)
+    w[[1, 4]] = 0.0
+    w /= w.sum()
+    dofs = np.linspace(3.0, 8.0, K)
+    live = [0, 2, 3, 5]
+    comps = orc.Components(means, covs, dofs)
+    rho_ref, _ = orc.calculate_rho_rb(x, comps, w, live)
+    gamma_ref = orc.student_t_gamma(x, comps, live)
+    mix = create_t_mixture(means, covs, dofs, w)
+    xd = torch.from_numpy(x).cuda()
+    rho = torch.zeros((N, K), dtype=torch.float64, device="cuda")
+    gam = torch.zeros((N, K), dtype=torch.float64, device="cuda")
+    run_k1(xd, mix._packed(live), K, _lib.MODE_STUDENT_T, resp=rho, aux=gam)
+    assert rel_err(rho.cpu().numpy(), rho_ref) < 1e-9
+    assert (rho.cpu().numpy()[:, [1, 4]] == 0).all()
+    assert rel_err(gam.cpu().numpy(), gamma_ref) < TOL
+
+
+def test_k2_vs_numpy_moments(pm):
+    """K2 alone against a float64 numpy evaluation of the same shifted raw moments."""
+    import torch
+    from pypmc_b200 import _lib
+    rng = np.random.default_rng(3)
+    for (K, D, N, use_g, use_w) in [(1, 1, 5, False, False), (3, 2, 77, True, True), (32, 30, 3001, False, True),
+                                    (64, 20, 2500, False, False), (16, 40, 1111, True, True), (5, 47, 400, True, False),
+                                    (130, 6, 999, False, True)]:
+        x = rng.normal(size=(N, D)) + 2.0
+        rho = rng.uniform(size=(N, K))
+        gam = rng.uniform(0.5, 2.0, size=(N, K)) if use_g else None
+        w = rng.uniform(0.5, 1.5, size=N) if use_w else None
+        shift = rng.normal(size=D)
+        T = D * (D + 1) // 2
+        out = torch.empty((K, 3 + D + T), dtype=torch.float64, device="cuda")
+        tod = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        _lib.Context.get().suffstats(tod(x), N, D, D, tod(shift), tod(rho), tod(gam), K, K, tod(w), out)
+        got = out.cpu().numpy()
+        u = rho * (1.0 if w is None else w[:, None])
+        v = u * (1.0 if gam is None else gam)
+        y = x - shift
+        il = np.tril_indices(D)
+        np.testing.assert_allclose(got[:, 0], u.sum(0), rtol=1e-12)
+        np.testing.assert_allclose(got[:, 1], v.sum(0), rtol=1e-12)
+        np.testing.assert_allclose(got[:, 2:2 + D], v.T @ y, rtol=1e-11, atol=1e-9)
+        R = np.einsum("nk,ni,nj->kij", v, y, y)
+        np.testing.assert_allclose(got[:, 2 + D:2 + D + T], R[:, il[0], il[1]], rtol=1e-11, atol=1e-9)
+        L = (u * np.log(gam)).sum(0) if use_g else np.zeros(K)
+        np.testing.assert_allclose(got[:, -1], L, rtol=1e-11, atol=1e-12)
+
+
+def test_full_size_properties(pm):
+    """BASELINE config 2 size (N=1e7 would take the oracle minutes): size-independent properties at N=2e6 --
+    permutation invariance of per-sample outputs, agreement of a shard-wise evaluation with the whole, and the
+    fused sum_n w_n log q_n against a float64 torch reduction of the per-sample output."""
+    import torch
+    from pypmc_b200.density.mixture import create_gaussian_mixture
+    from pypmc_b200.density._eval import run_k1
+    from pypmc_b200 import _lib
+    K, D, N = 32, 30, 2_000_000
+    means, covs, w, x_small, _ = _synth(K, D, 1000, seed=11)
+    mix = create_gaussian_mixture(means, covs, w)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn((N, D), dtype=torch.float64, device="cuda", generator=g) * 2.0
+    lq = mix.multi_evaluate(x)
+    perm = torch.randperm(N, device="cuda", generator=g)
+    lq_perm = mix.multi_evaluate(x[perm].contiguous())
+    assert torch.equal(lq_perm, lq[perm])
+    half = N // 2 + 17
+    assert torch.equal(mix.multi_evaluate(x[:half]), lq[:half])
+    assert torch.equal(mix.multi_evaluate(x[half:]), lq[half:])
+    sw = torch.rand(N, dtype=torch.float64, device="cuda", generator=g)
+    sums = run_k1(x, mix._packed(), K, _lib.MODE_GAUSS, weights=sw, want_sums=True).cpu().numpy()
+    assert sums[0] == pytest.approx(float((sw * lq).sum()), rel=1e-12)
+    assert sums[1] == pytest.approx(float(sw.sum()), rel=1e-12)
+    # linear-domain check of rho: rows sum to one where nothing underflows
+    rho = torch.empty((N, K), dtype=torch.float64, device="cuda")
+    run_k1(x, mix._packed(), K, _lib.MODE_GAUSS, resp=rho)
+    ok = lq > -600
+    assert float((rho.sum(1)[ok] - 1.0).abs().max()) < 1e-12
