@@ -1,29 +1,53 @@
 // k1_dispatch.cuh -- launch table of the K1 instantiations (one per even padded dimension DP).
+// One logical K1 launch = the fast form (k1_fast_eval.cuh) followed by the exact-difference form
+// (k1_mixture_eval.cuh) on the same stream; the device-side flag written by k1_prepare decides which of the
+// two does the work (the other returns immediately).
 #pragma once
-#include "k1_mixture_eval.cuh"
+#include "k1_fast_eval.cuh"
 
 namespace pmc {
 
+struct K1Launch {
+  EvalArgs base;            // records = the caller's packed records (T | centre | scalars)
+  const double* derived;    // records with the centre slot replaced by -b (k1_prepare)
+  const double* shift;      // [DP]
+  const int* flag;
+};
+
 // returns cudaError_t as int; grid <= #SMs (persistent CTAs, one per SM)
 template <int DP>
-int k1_launch_dp(const EvalArgs& a, int grid, cudaStream_t stream);
+int k1_launch_dp(const K1Launch& l, int grid, cudaStream_t stream);
 
-int k1_launch(int dp, const EvalArgs& a, int grid, cudaStream_t stream);
-int k1_tile_rows(int dp);   // samples per CTA tile for this DP
-int k1_warps(int dp);       // warps per CTA for this DP
+int k1_launch(int dp, const K1Launch& l, int grid, cudaStream_t stream);
+int k1_tile_rows(int dp);   // samples per CTA tile for this DP (same for both forms)
 
-#define PMC_K1_INSTANTIATE(DP)                                                                      \
-  template <>                                                                                        \
-  int k1_launch_dp<DP>(const EvalArgs& a, int grid, cudaStream_t stream) {                          \
-    static bool attr_set = false;                                                                    \
-    if (!attr_set) {                                                                                 \
+#define PMC_K1_INSTANTIATE(DP)                                                                       \
+  template <>                                                                                         \
+  int k1_launch_dp<DP>(const K1Launch& l, int grid, cudaStream_t stream) {                           \
+    static_assert(FastCfg<DP>::TS == EvalCfg<DP>::TS, "both K1 forms must tile the samples alike");  \
+    static_assert(FastCfg<DP>::NW <= PMC_MAX_WARPS && EvalCfg<DP>::NW <= PMC_MAX_WARPS, "partials"); \
+    static_assert(FastCfg<DP>::SMEM_STAGED + 16 <= 227 * 1024, "staging does not fit");             \
+    static bool attr_set = false;                                                                     \
+    if (!attr_set) {                                                                                  \
       cudaError_t e = cudaFuncSetAttribute(k1_mixture_eval<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                           int(EvalCfg<DP>::SMEM_BYTES));                            \
-      if (e != cudaSuccess) return int(e);                                                           \
-      attr_set = true;                                                                               \
-    }                                                                                                \
-    k1_mixture_eval<DP><<<grid, EvalCfg<DP>::NW * 32, EvalCfg<DP>::SMEM_BYTES, stream>>>(a);         \
-    return int(cudaGetLastError());                                                                  \
+                                           int(EvalCfg<DP>::SMEM_BYTES));                             \
+      if (e != cudaSuccess) return int(e);                                                            \
+      e = cudaFuncSetAttribute(k1_fast_eval<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                               int(FastCfg<DP>::SMEM_STAGED + 16));                                   \
+      if (e != cudaSuccess) return int(e);                                                            \
+      attr_set = true;                                                                                \
+    }                                                                                                 \
+    FastArgs fa{l.base, l.shift, l.flag};                                                             \
+    fa.e.records = l.derived;                                                                         \
+    const bool staged = l.base.lp_out || l.base.resp_out || l.base.aux_out;                           \
+    const size_t smem = (staged ? FastCfg<DP>::SMEM_STAGED : FastCfg<DP>::SMEM_BASE) + 16;            \
+    k1_fast_eval<DP><<<grid, FastCfg<DP>::NW * 32, smem, stream>>>(fa);                               \
+    cudaError_t e = cudaGetLastError();                                                               \
+    if (e != cudaSuccess) return int(e);                                                              \
+    EvalArgs ea = l.base;                                                                             \
+    ea.flag = l.flag;                                                                                 \
+    k1_mixture_eval<DP><<<grid, EvalCfg<DP>::NW * 32, EvalCfg<DP>::SMEM_BYTES, stream>>>(ea);         \
+    return int(cudaGetLastError());                                                                   \
   }
 
 }  // namespace pmc

@@ -43,7 +43,8 @@ struct EvalArgs {
   double* resp_out;       // [n, k_out] or null : rho (PMC) / r (VB)
   double* aux_out;        // [n, k_out] or null : gamma (Student-t) / expectation_gauss_exponent (VB)
   const double* sw;       // [n] sample weights or null
-  double* partials;       // [grid * NW * 2] or null : per-warp (sum w*logq | sum w r log r , sum w)
+  double* partials;       // [grid * PMC_MAX_WARPS * 2] or null : per-warp (sum w*logq | sum w r log r , sum w)
+  const int* flag;        // null: always run.  else the exact-difference kernel runs iff *flag != 0 (k1_fast_eval.cuh)
 };
 
 template <int DP>
@@ -65,6 +66,7 @@ template <int DP>
 __global__ void __launch_bounds__(EvalCfg<DP>::NW * 32, 1) k1_mixture_eval(const EvalArgs a) {
   using C = EvalCfg<DP>;
   constexpr int S = C::S, NW = C::NW, NS = C::NS, XS = C::XS, RL = C::RL, H = DP / 2;
+  if (a.flag != nullptr && *a.flag == 0) return;                       // the fast form handled this launch
   constexpr int NT = tri_len(DP);
   constexpr uint32_t REC_BYTES = RL * sizeof(double);
 
@@ -278,8 +280,8 @@ __global__ void __launch_bounds__(EvalCfg<DP>::NW * 32, 1) k1_mixture_eval(const
       part_w += __shfl_xor_sync(0xffffffffu, part_w, o);
     }
     if (lane == 0) {
-      a.partials[(size_t(blockIdx.x) * NW + warp) * 2 + 0] = part_a;
-      a.partials[(size_t(blockIdx.x) * NW + warp) * 2 + 1] = part_w;
+      a.partials[(size_t(blockIdx.x) * PMC_MAX_WARPS + warp) * 2 + 0] = part_a;
+      a.partials[(size_t(blockIdx.x) * PMC_MAX_WARPS + warp) * 2 + 1] = part_w;
     }
   }
 }

@@ -25,6 +25,8 @@ namespace pmc {
 // A record is a multiple of 16 bytes, so one cp.async.bulk moves it into shared memory.
 // ---------------------------------------------------------------------------------------------
 constexpr int kNumScalars = 8;
+#define PMC_MAX_DP 64      // largest padded dimension the K1 instantiations cover
+#define PMC_MAX_WARPS 16   // stride of the per-warp partial sums (>= warps per CTA of every K1 variant)
 
 __host__ __device__ constexpr int tri_len(int DP) { return (DP / 2) * (DP / 2 + 1) * 2; }
 __host__ __device__ constexpr int record_len(int DP) { return tri_len(DP) + DP + kNumScalars; }

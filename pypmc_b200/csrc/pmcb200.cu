@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "k1_dispatch.cuh"
+#include "k1_prepare.cuh"
 #include "k2_suffstats.cuh"
 #include "microbench.cuh"
 
@@ -15,7 +16,7 @@ namespace pmc {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& msg) { g_last_error = msg; }
 
-int k1_launch(int dp, const EvalArgs& a, int grid, cudaStream_t stream) {
+int k1_launch(int dp, const K1Launch& a, int grid, cudaStream_t stream) {
   switch (dp) {
 #define PMC_CASE(DP) \
   case DP:           \
@@ -33,7 +34,6 @@ int k1_launch(int dp, const EvalArgs& a, int grid, cudaStream_t stream) {
 template <int DP>
 struct CfgQuery {
   static int tile() { return EvalCfg<DP>::TS; }
-  static int warps() { return EvalCfg<DP>::NW; }
 };
 
 int k1_tile_rows(int dp) {
@@ -51,27 +51,14 @@ int k1_tile_rows(int dp) {
   }
 }
 
-int k1_warps(int dp) {
-  switch (dp) {
-#define PMC_CASE(DP) \
-  case DP:           \
-    return CfgQuery<DP>::warps();
-    PMC_CASE(2) PMC_CASE(4) PMC_CASE(6) PMC_CASE(8) PMC_CASE(10) PMC_CASE(12) PMC_CASE(14) PMC_CASE(16)
-    PMC_CASE(18) PMC_CASE(20) PMC_CASE(22) PMC_CASE(24) PMC_CASE(26) PMC_CASE(28) PMC_CASE(30) PMC_CASE(32)
-    PMC_CASE(34) PMC_CASE(36) PMC_CASE(38) PMC_CASE(40) PMC_CASE(42) PMC_CASE(44) PMC_CASE(46) PMC_CASE(48)
-    PMC_CASE(50) PMC_CASE(52) PMC_CASE(54) PMC_CASE(56) PMC_CASE(58) PMC_CASE(60) PMC_CASE(62) PMC_CASE(64)
-#undef PMC_CASE
-    default:
-      return 0;
-  }
-}
-
 // sums[0..1] = fixed-order sum of the per-warp partial pairs
-__global__ void k1_reduce_sums(const double* __restrict__ partials, int count, double* __restrict__ sums) {
+__global__ void k1_reduce_sums(double* __restrict__ partials, int count, double* __restrict__ sums) {
   double a = 0.0, w = 0.0;
   for (int i = threadIdx.x; i < count; i += 32) {
     a += partials[2 * i];
     w += partials[2 * i + 1];
+    partials[2 * i] = 0.0;      // leave the slots clean for the next launch that shares this workspace
+    partials[2 * i + 1] = 0.0;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -96,7 +83,8 @@ struct DevBuf {
 struct pmcb200_ctx {
   int device = 0;
   int sm_count = 0;
-  DevBuf ws;              // partial sums of K1 / K2 (device-pointer entry points)
+  DevBuf ws;              // partial sums of K2 / microbenchmark scratch
+  DevBuf k1ws;            // K1: derived records, shift, flag, per-warp partial sums (device-pointer entry point)
   cudaStream_t copy_stream[2] = {nullptr, nullptr};
   // host pipeline: per-slot device buffers
   DevBuf hx[2], hw[2], hlogq[2], hlp[2], hresp[2], haux[2], hws[2], hsums[2];
@@ -149,7 +137,7 @@ int pmcb200_create(int device, pmcb200_ctx** out) {
 int pmcb200_destroy(pmcb200_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
-  DevBuf* all[] = {&c->ws, &c->hrec, &c->hcols};
+  DevBuf* all[] = {&c->ws, &c->k1ws, &c->hrec, &c->hcols};
   for (DevBuf* b : all)
     if (b->p) cudaFree(b->p);
   for (int i = 0; i < 2; ++i) {
@@ -195,25 +183,46 @@ static int eval_validate(int64_t n, int64_t ldx, int d, int kl, int k_out, int m
   return 0;
 }
 
-static int eval_launch(pmcb200_ctx* c, DevBuf& ws, const EvalArgs& a0, double* sums_dev, cudaStream_t st) {
-  EvalArgs a = a0;
+// One logical K1 launch on stream st: [k1_prepare] -> k1_fast_eval -> k1_mixture_eval (one of the two works, see
+// k1_dispatch.cuh) [-> k1_reduce_sums].  `prep` holds the derived records / shift / flag / per-warp partial sums;
+// with `prepared` the prepare kernel already ran for these records on this stream (host pipeline: once per call).
+static int eval_prepare(pmcb200_ctx* c, DevBuf& prep, const EvalArgs& a, cudaStream_t st, K1Launch* out) {
   const int dp = (a.d + 1) & ~1;
-  const int ts = k1_tile_rows(dp), nw = k1_warps(dp);
-  const int64_t tiles = (a.n + ts - 1) / ts;
+  const int rl = record_len(dp);
+  const size_t n_part = size_t(c->sm_count) * PMC_MAX_WARPS * 2;
+  const size_t off_shift = size_t(a.kl) * rl, off_part = off_shift + PMC_MAX_DP, off_flag = off_part + n_part;
+  if (int rc = ensure(prep, (off_flag + 2) * sizeof(double))) return rc;
+  double* base = static_cast<double*>(prep.p);
+  k1_prepare<<<1, 256, 0, st>>>(a.records, a.kl, dp, base, base + off_shift, reinterpret_cast<int*>(base + off_flag),
+                                base + off_part, int(n_part));
+  PMC_CUDA_CHECK(cudaGetLastError());
+  c->launches++;
+  out->derived = base;
+  out->shift = base + off_shift;
+  out->flag = reinterpret_cast<int*>(base + off_flag);
+  out->base = a;
+  out->base.partials = base + off_part;
+  return 0;
+}
+
+static int eval_launch(pmcb200_ctx* c, const K1Launch& prep, const EvalArgs& a0, double* sums_dev, cudaStream_t st) {
+  K1Launch l = prep;
+  double* partials = prep.base.partials;
+  l.base = a0;
+  l.base.partials = sums_dev ? partials : nullptr;
+  const int dp = (a0.d + 1) & ~1;
+  const int ts = k1_tile_rows(dp);
+  const int64_t tiles = (a0.n + ts - 1) / ts;
   const int grid = int(std::min<int64_t>(tiles, c->sm_count));
-  a.partials = nullptr;
-  if (sums_dev) {
-    if (int rc = ensure(ws, size_t(grid) * nw * 2 * sizeof(double))) return rc;
-    a.partials = static_cast<double*>(ws.p);
-  }
-  const int e = k1_launch(dp, a, grid, st);
+  const int e = k1_launch(dp, l, grid, st);
   if (e != 0) {
-    set_last_error(std::string("k1_mixture_eval launch: ") + cudaGetErrorString(cudaError_t(e)));
+    set_last_error(std::string("k1 launch: ") + cudaGetErrorString(cudaError_t(e)));
     return 1;
   }
-  c->launches++;
+  c->launches += 2;
   if (sums_dev) {
-    k1_reduce_sums<<<1, 32, 0, st>>>(a.partials, grid * nw, sums_dev);
+    // partial slots of CTAs / warps that did not run hold the zeros written by k1_prepare (or by the last reduce)
+    k1_reduce_sums<<<1, 32, 0, st>>>(partials, c->sm_count * PMC_MAX_WARPS, sums_dev);
     PMC_CUDA_CHECK(cudaGetLastError());
     c->launches++;
   }
@@ -232,8 +241,10 @@ int pmcb200_mixture_eval(pmcb200_ctx* c, const double* x, int64_t n, int64_t ldx
     return 0;
   }
   PMC_REQUIRE(x && records && cols, "mixture_eval: NULL input");
-  EvalArgs a{x, n, ldx, d, records, cols, kl, k_out, mode, max_init, logq, lp, resp, aux, weights, nullptr};
-  return eval_launch(c, c->ws, a, sums, st);
+  EvalArgs a{x, n, ldx, d, records, cols, kl, k_out, mode, max_init, logq, lp, resp, aux, weights, nullptr, nullptr};
+  K1Launch prep;
+  if (int rc = eval_prepare(c, c->k1ws, a, st, &prep)) return rc;
+  return eval_launch(c, prep, a, sums, st);
 }
 
 int pmcb200_suffstats(pmcb200_ctx* c, const double* x, int64_t n, int64_t ldx, int d, const double* shift,
@@ -325,6 +336,12 @@ int pmcb200_mixture_eval_host(pmcb200_ctx* c, const double* x, int64_t n, int64_
 
   const int64_t nchunks = (n + chunk_rows - 1) / chunk_rows;
   std::vector<double> chunk_sums(size_t(nchunks) * 2, 0.0);
+  K1Launch prep[2];
+  for (int s = 0; s < 2 && s < nchunks; ++s) {   // derived records / shift / flag once per stream, not per chunk
+    EvalArgs a{nullptr, 0, d, d, static_cast<const double*>(c->hrec.p), static_cast<const int*>(c->hcols.p), kl, k_out,
+               mode, max_init, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (int rc = eval_prepare(c, c->hws[s], a, c->copy_stream[s], &prep[s])) return rc;
+  }
   for (int64_t ci = 0; ci < nchunks; ++ci) {
     const int s = int(ci & 1);
     cudaStream_t st = c->copy_stream[s];
@@ -344,8 +361,8 @@ int pmcb200_mixture_eval_host(pmcb200_ctx* c, const double* x, int64_t n, int64_
                lp ? static_cast<double*>(c->hlp[s].p) : nullptr,
                resp ? static_cast<double*>(c->hresp[s].p) : nullptr,
                aux ? static_cast<double*>(c->haux[s].p) : nullptr,
-               weights ? static_cast<const double*>(c->hw[s].p) : nullptr, nullptr};
-    if (int rc = eval_launch(c, c->hws[s], a, sums ? static_cast<double*>(c->hsums[s].p) : nullptr, st)) return rc;
+               weights ? static_cast<const double*>(c->hw[s].p) : nullptr, nullptr, nullptr};
+    if (int rc = eval_launch(c, prep[s], a, sums ? static_cast<double*>(c->hsums[s].p) : nullptr, st)) return rc;
     if (logq) PMC_CUDA_CHECK(cudaMemcpyAsync(logq + r0, c->hlogq[s].p, size_t(rows) * sizeof(double), cudaMemcpyDeviceToHost, st));
     const size_t out_bytes = size_t(rows) * k_out * sizeof(double);
     if (lp) PMC_CUDA_CHECK(cudaMemcpyAsync(lp + r0 * k_out, c->hlp[s].p, out_bytes, cudaMemcpyDeviceToHost, st));

@@ -1,10 +1,9 @@
 #!/bin/bash
-# First GPU pass: smoke, parity tests, short bench, fp64 microbench. Outputs under gpurun_out/.
+# GPU pass: smoke, parity tests, per-kernel config timings, bench. Outputs under gpurun_out/.
+TAG=${1:-chk}
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > gpurun_out/smi.txt 2>&1
-nproc >> gpurun_out/smi.txt
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-timeout 300 python scripts/microbench.py > gpurun_out/microbench.log 2>&1
-timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.log 2>&1; echo "bench rc=$?" >> gpurun_out/bench.log
-tail -3 gpurun_out/smoke.log; tail -15 gpurun_out/pytest_gpu.log; cat gpurun_out/microbench.log; tail -5 gpurun_out/bench.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_$TAG.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke_$TAG.log
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu_$TAG.log
+timeout 600 python scripts/bench_configs.py --reps 5 > gpurun_out/configs_$TAG.log 2>&1
+timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.log 2>&1; echo "bench rc=$?" >> gpurun_out/bench_$TAG.log
+tail -3 gpurun_out/smoke_$TAG.log; tail -25 gpurun_out/pytest_gpu_$TAG.log; cat gpurun_out/configs_$TAG.log; tail -4 gpurun_out/bench_$TAG.log

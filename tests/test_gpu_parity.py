@@ -117,7 +117,10 @@ def test_gauss_mixture_fixture(pm, golden, name):
     # components subset only touches its columns (mixture.pyx:153-156)
     ind2 = np.full((n, k), -7.0)
     assert mix.multi_evaluate(x, individual=ind2, components=[1, k - 1]) is None
-    np.testing.assert_array_equal(ind2[:, [1, k - 1]], ind[:, [1, k - 1]])
+    # (the shift c of the fast K1 form is the weighted centre of the EVALUATED components, so a subset agrees
+    # with the full evaluation to rounding, not bit for bit; the reference only pins bitwise equality across the
+    # out / individual variants above)
+    np.testing.assert_allclose(ind2[:, [1, k - 1]], ind[:, [1, k - 1]], rtol=1e-13, atol=0)
     assert (np.delete(ind2, [1, k - 1], axis=1) == -7.0).all()
 
 
@@ -254,7 +257,7 @@ def test_k1_vs_oracle_shapes(pm, orc, K, D, N):
         col = np.empty((N, K))
         for k, c in enumerate(mix.components):
             c.multi_evaluate(x, col[:, k])
-        np.testing.assert_array_equal(col, ind)
+        np.testing.assert_allclose(col, ind, rtol=1e-13, atol=0)   # K = 1 launch: shift = mu_k, so rounding-level only
 
 
 def test_rho_gamma_vs_oracle_with_dead_components(pm, orc):
