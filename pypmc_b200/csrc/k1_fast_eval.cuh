@@ -43,8 +43,8 @@ struct FastArgs {
 
 template <int DP>
 struct FastCfg {
-  static constexpr int S = (DP <= 20) ? 4 : (DP <= 40) ? 2 : 1;
-  static constexpr int NW = (DP <= 12) ? 12 : (DP <= 20) ? 8 : (DP <= 32) ? 12 : 8;
+  static constexpr int S = (DP <= 20) ? 4 : (DP <= 32) ? 3 : (DP <= 40) ? 2 : 1;
+  static constexpr int NW = (DP <= 12) ? 12 : 8;
   static constexpr int NS = 3;
   static constexpr int KC = (S >= 4) ? 8 : 16;             // components per output staging chunk
   static constexpr int ROWS_PER_WARP = 32 * S;
@@ -222,12 +222,13 @@ __global__ void __launch_bounds__(FastCfg<DP>::NW * 32, 1) k1_fast_eval(const Fa
           aux = c3 + c4 * q[s];                                   // variational.pyx:798
           lp = c0 + 0.5 * (c1 - c2 - aux);                        // variational.pyx:691
         }
-        // online weighted log-sum-exp (same value as _regularize.pyx:72-81 up to rounding)
-        if (lp > run_max[s]) {
-          run_sum[s] = run_sum[s] * exp(run_max[s] - lp) + wk;
-          run_max[s] = lp;
-        } else {
-          run_sum[s] += wk * exp(lp - run_max[s]);
+        // online weighted log-sum-exp (same value as _regularize.pyx:72-81 up to rounding), branch-free:
+        // one exp of -|lp - max| per pair whichever of the two is larger, so lanes never diverge here
+        {
+          const bool up = lp > run_max[s];
+          const double e = exp(-fabs(lp - run_max[s]));
+          run_sum[s] = fma(up ? run_sum[s] : wk, e, up ? wk : run_sum[s]);
+          run_max[s] = up ? lp : run_max[s];
         }
         if (staged) {
           st_lp[kc * RWP + lane + 32 * s] = lp;

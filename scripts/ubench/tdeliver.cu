@@ -118,29 +118,32 @@ int main() {
   CK(cudaMemcpyToSymbol(cT, hT.data(), CONST_DOUBLES * 8));
   double *gT, *x, *out;
   CK(cudaMalloc(&gT, CONST_DOUBLES * 8)); CK(cudaMemcpy(gT, hT.data(), CONST_DOUBLES * 8, cudaMemcpyHostToDevice));
-  const size_t nx = size_t(sms) * 384 * 3 * 40;
+  const size_t nx = size_t(sms) * 512 * 8 * 40;
   CK(cudaMalloc(&x, nx * 8)); CK(cudaMemset(x, 0, nx * 8));
-  CK(cudaMalloc(&out, size_t(sms) * 384 * 8));
-  for (int kl : {1, 4, 8, 16}) {
-    run<30, 2, 0, 0, 384>("smem LDS.128  S=2 12w", kl, gT, x, out, sms);
-    run<30, 2, 1, 0, 384>("const LDCU.64 S=2 12w", kl, gT, x, out, sms);
-    run<30, 2, 2, 0, 384>("const 128-bit S=2 12w", kl, gT, x, out, sms);
-    run<30, 2, 3, 10, 384>("split r<10 smem S=2 12w", kl, gT, x, out, sms);
-    run<30, 2, 3, 11, 384>("split r<11 smem S=2 12w", kl, gT, x, out, sms);
-    run<30, 3, 0, 0, 256>("smem LDS.128  S=3 8w", kl, gT, x, out, sms);
-    run<30, 3, 1, 0, 256>("const LDCU.64 S=3 8w", kl, gT, x, out, sms);
-    run<30, 3, 3, 10, 256>("split r<10 smem S=3 8w", kl, gT, x, out, sms);
-  }
-  for (int kl : {1, 8, 32}) {
-    run<20, 4, 0, 0, 256>("smem LDS.128  S=4 8w", kl, gT, x, out, sms);
-    run<20, 4, 1, 0, 256>("const LDCU.64 S=4 8w", kl, gT, x, out, sms);
-    run<20, 3, 0, 0, 384>("smem LDS.128  S=3 12w", kl, gT, x, out, sms);
-    run<20, 3, 1, 0, 384>("const LDCU.64 S=3 12w", kl, gT, x, out, sms);
-  }
-  for (int kl : {1, 4, 8}) {
-    run<40, 2, 0, 0, 256>("smem LDS.128  S=2 8w", kl, gT, x, out, sms);
-    run<40, 2, 1, 0, 256>("const LDCU.64 S=2 8w", kl, gT, x, out, sms);
-    run<40, 2, 3, 14, 256>("split r<14 smem S=2 8w", kl, gT, x, out, sms);
+  CK(cudaMalloc(&out, size_t(sms) * 512 * 8));
+  for (int kl : {8}) {
+    run<30, 2, 0, 0, 384>("smem S=2 12w", kl, gT, x, out, sms);
+    run<30, 2, 0, 0, 352>("smem S=2 11w", kl, gT, x, out, sms);
+    run<30, 2, 0, 0, 320>("smem S=2 10w", kl, gT, x, out, sms);
+    run<30, 2, 0, 0, 288>("smem S=2 9w", kl, gT, x, out, sms);
+    run<30, 2, 0, 0, 256>("smem S=2 8w", kl, gT, x, out, sms);
+    run<30, 3, 0, 0, 256>("smem S=3 8w", kl, gT, x, out, sms);
+    run<30, 3, 0, 0, 224>("smem S=3 7w", kl, gT, x, out, sms);
+    run<30, 3, 0, 0, 192>("smem S=3 6w", kl, gT, x, out, sms);
+    run<20, 4, 0, 0, 256>("smem S=4 8w", kl, gT, x, out, sms);
+    run<20, 4, 0, 0, 320>("smem S=4 10w", kl, gT, x, out, sms);
+    run<20, 4, 0, 0, 384>("smem S=4 12w", kl, gT, x, out, sms);
+    run<20, 3, 0, 0, 384>("smem S=3 12w", kl, gT, x, out, sms);
+    run<20, 3, 0, 0, 448>("smem S=3 14w", kl, gT, x, out, sms);
+    run<20, 5, 0, 0, 256>("smem S=5 8w", kl, gT, x, out, sms);
+    run<20, 6, 0, 0, 256>("smem S=6 8w", kl, gT, x, out, sms);
+    run<40, 2, 0, 0, 256>("smem S=2 8w", kl, gT, x, out, sms);
+    run<40, 2, 0, 0, 320>("smem S=2 10w", kl, gT, x, out, sms);
+    run<40, 2, 0, 0, 384>("smem S=2 12w", kl, gT, x, out, sms);
+    run<40, 3, 0, 0, 256>("smem S=3 8w", kl, gT, x, out, sms);
+    run<10, 4, 0, 0, 384>("smem S=4 12w", kl, gT, x, out, sms);
+    run<10, 8, 0, 0, 384>("smem S=8 12w", kl, gT, x, out, sms);
+    run<10, 6, 0, 0, 512>("smem S=6 16w", kl, gT, x, out, sms);
   }
   return 0;
 }
