@@ -12,25 +12,31 @@
 // mixture so that the raw moments do not cancel badly).  The host turns (A, B, m, R) into the reference's
 // two-pass quantities: delta = m/B, mean = shift + delta, cov = (R - B delta delta^T) / A.
 //
-// Shape of the computation: Out[k, f] = sum_n V[n, k] * Phi[n, f], with the feature vector
-// Phi_n = [1, y_n, tril(y_n y_n^T)] of length F = 1 + D + D(D+1)/2 -- a (K x N) x (N x F) product whose
-// B operand is built on the fly in shared memory (D(D+1)/2 multiplies per sample, shared by all K
-// components).  K F FP64 FMAs per sample against 8 (D + K) bytes: DFMA-pipe bound like K1.
+// Shape of the computation: K symmetric rank-N updates sharing one y (plus the linear terms sum v y, sum v):
+// (D+1)(D+2)/2 FP64 FMAs per sample-component against 8 (D + K) bytes per sample: DFMA-pipe bound like K1.
 //
-// Mapping: a warp owns a 16 (components) x 128 (features) block of Out, each lane a 16 x 4 register tile
-// (64 accumulators).  Per sample a lane issues 8 broadcast LDS.128 (16 v's) + 2 LDS.128 (4 phi's) for 64
-// DFMAs.  CTAs are persistent over sample tiles; each CTA writes one partial Out block, and a second
-// tiny kernel adds the partials in CTA order -- no floating-point atomics, so results are reproducible
-// run to run for a given grid.
+// Mapping (round 1 profile: the first K2 staged a [samples x features] product table in shared memory behind
+// three block-wide barriers per 44-sample tile and reached 18 % of the DFMA peak): a thread owns, for 16
+// components (64 accumulators), either one 2x2 block (row pair r, column pair p <= r) of the lower triangle of
+// y y^T, or four consecutive entries of the linear row [y, 1] (m_k and B_k).  Per sample it reads the 16 v's
+// (8 broadcast LDS.128) and two pairs of the sample row (2 LDS.128), forms its 4 features in registers (4 DMUL
+// + selects) and issues 64 DFMAs; no product table exists anywhere.  Lane tiles are numbered
+// t = kgroup * (Bq + Lq) + tile (Bq = P0(P0+1)/2 blocks, P0 = ceil(D/2); Lq = ceil((D+1)/4) quads) and dealt to
+// 8 warps per CTA -- two per SM sub-partition, the only warp count that both leaves 255 registers per thread
+// and loads the four schedulers evenly; K=32, D=30 gives exactly 256 lane tiles.  If there are more,
+// gridDim.y CTAs share the same samples.  Samples stream through a two-stage shared-memory pipeline:
+// raw rho / gamma / x / w rows arrive with cp.async (LDGSTS) one tile ahead, a short in-place pass turns them
+// into v and yh, and the block-wide barriers are per 128-sample tile (~37k clk of DFMA work).
+// Each CTA writes one partial block; a second tiny kernel adds the partials in CTA order -- no floating-point
+// atomics, so results are reproducible run to run for a given grid.
 #pragma once
 
 #include "pmc_common.cuh"
 
 namespace pmc {
 
-constexpr int K2_TK = 16;    // components per warp block
-constexpr int K2_TF = 128;   // features per warp block
-constexpr int K2_MAX_WARPS = 8;
+constexpr int K2_TK = 16;          // components per lane tile
+constexpr int K2_MAX_THREADS = 256;  // 8 warps, two per SM sub-partition
 
 struct StatsArgs {
   const double* x;      // [n, ldx]
@@ -44,144 +50,193 @@ struct StatsArgs {
   int k;                // number of components (columns used)
   int ld_rho;
   int F;                // 1 + d + d(d+1)/2
-  int units_k, units_f; // ceil(k/16), ceil(F/128)
-  int wk, wf;           // warp grid of one CTA (wk * wf warps)
-  int tn;               // samples per tile
+  int P0;               // ceil(d/2): pairs of y
+  int Bq;               // P0(P0+1)/2 quadratic blocks per component group
+  int Lq;               // ceil((d+1)/4) quads of the linear row [y, 1]
+  int DP4;              // d+1 rounded up to a multiple of 4: row length of the staged samples
+  int KP;               // k rounded up to a multiple of 16
+  int LT;               // lane tiles = (KP/16) * (Bq + Lq)
+  int tn;               // samples per tile (multiple of 2)
   double* partial;      // [gridDim.x, k, F+2]   (column 0 = A, column 1+f = Out[k,f], column F+1 = sum w rho ln gamma)
 };
 
-__global__ void __launch_bounds__(K2_MAX_WARPS * 32, 1) k2_suffstats(const StatsArgs a) {
+__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(K2_MAX_THREADS, 1) k2_suffstats(const StatsArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int nwarps = a.wk * a.wf;
-  const int nthreads = nwarps * 32;
-  const int KC = a.wk * K2_TK;          // components covered by this CTA (padded)
-  const int FC = a.wf * K2_TF;          // features covered by this CTA (padded)
-  const int chunk_k = blockIdx.y % ((a.units_k + a.wk - 1) / a.wk);
-  const int chunk_f = blockIdx.y / ((a.units_k + a.wk - 1) / a.wk);
-  const int k0 = chunk_k * KC, f0 = chunk_f * FC;
-  const int D = a.d, TN = a.tn;
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  const int D = a.d, KP = a.KP, DP2 = a.DP4, TN = a.tn;
+  const bool has_g = a.gamma != nullptr;
 
-  double* ytile = reinterpret_cast<double*>(smem_raw);     // [TN][D]
-  double* vtile = ytile + ((TN * D + 1) & ~1);             // [TN][KC]   w rho gamma
-  double* atile = vtile + TN * KC;                         // [TN][KC]   w rho        (only if gamma)
-  double* ltile = atile + (a.gamma ? TN * KC : 0);         // [TN][KC]   w rho ln(gamma) (only if gamma)
-  double* phi = ltile + (a.gamma ? TN * KC : 0);           // [TN][FC]
-  short2* fmap = reinterpret_cast<short2*>(phi + size_t(TN) * FC);  // [FC] feature -> (i, j)
+  // stage layout (doubles): V [TN][KP] | G [TN][KP] (gamma only) | Y [TN][DP2] | W [TN]
+  const int stage_len = TN * KP * (has_g ? 2 : 1) + TN * DP2 + TN;
+  double* stage0 = reinterpret_cast<double*>(smem_raw);
+  double* shift_s = stage0 + 2 * stage_len;                       // [DP2]
+  double* colsum = shift_s + DP2;                                 // gamma only: [nwarps][2][KP] column sums of w rho, w rho ln(gamma)
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
+  for (int j = tid; j < DP2; j += nthreads) shift_s[j] = (j < D) ? a.shift[j] : 0.0;
+  if (has_g)
+    for (int e = tid; e < nwarps * 2 * KP; e += nthreads) colsum[e] = 0.0;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int wkid = warp % a.wk, wfid = warp / a.wk;
-
-  // feature map: f = 0 -> (-1,-1) [constant 1];  1..D -> (i,-1) [y_i];  then (i,j), j<=i;  beyond F -> (-2,-2) [0]
-  for (int fl = tid; fl < FC; fl += nthreads) {
-    const int f = f0 + fl;
-    short2 ij;
-    if (f == 0) ij = make_short2(-1, -1);
-    else if (f <= D) ij = make_short2(short(f - 1), -1);
-    else if (f < a.F) {
-      const int t = f - 1 - D;
-      int i = int((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-      while ((i + 1) * (i + 2) / 2 <= t) ++i;
-      while (i * (i + 1) / 2 > t) --i;
-      ij = make_short2(short(i), short(t - i * (i + 1) / 2));
-    } else ij = make_short2(-2, -2);
-    fmap[fl] = ij;
+  // ---- this thread's lane tile ----
+  const int t = blockIdx.y * nthreads + tid;
+  const bool active = t < a.LT;
+  const int tt = active ? t : 0;
+  const int per_group = a.Bq + a.Lq;
+  const int kg = tt / per_group, b = tt - kg * per_group;
+  const bool lin = b >= a.Bq;                     // linear tile: entries 4q .. 4q+3 of [y, 1]
+  int r = 0, p = 0;
+  if (!lin) {
+    r = int((sqrt(8.0 * b + 1.0) - 1.0) * 0.5);
+    while ((r + 1) * (r + 2) / 2 <= b) ++r;
+    while (r * (r + 1) / 2 > b) --r;
+    p = b - r * (r + 1) / 2;
   }
+  const int off_a = lin ? 4 * (b - a.Bq) + 2 : 2 * r;    // second pair (linear) / row pair (quadratic)
+  const int off_b = lin ? 4 * (b - a.Bq) : 2 * p;        // first pair (linear) / column pair (quadratic)
 
   double acc[K2_TK][4];
 #pragma unroll
   for (int i = 0; i < K2_TK; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-  double acc_a = 0.0, acc_l = 0.0;  // A_k and sum w rho ln(gamma) for thread tid < KC (chunk_f == 0, gamma != null)
 
   const int64_t num_tiles = (a.n + TN - 1) / TN;
-  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+
+  auto issue_loads = [&](int64_t tile, double* st) {
     const int64_t row0 = tile * TN;
-    __syncthreads();  // previous tile fully consumed
-    // ---- y tile (coalesced over the contiguous rows) ----
-    for (int e = tid; e < TN * D; e += nthreads) {
-      const int r = e / D, j = e - r * D;
-      const int64_t row = row0 + r;
-      ytile[e] = (row < a.n) ? (__ldg(a.x + row * a.ldx + j) - __ldg(a.shift + j)) : 0.0;
+    const int rows = int((a.n - row0 < TN) ? (a.n - row0) : TN);
+    double* Vs = st;
+    double* Gs = st + TN * KP;
+    double* Ys = st + TN * KP * (has_g ? 2 : 1);
+    double* Ws = Ys + TN * DP2;
+    for (int rr = warp; rr < rows; rr += nwarps) {          // one warp per sample row, lanes over columns
+      const double* rp = a.rho + (row0 + rr) * a.ld_rho;
+      for (int kk = lane; kk < a.k; kk += 32) cp_async8(Vs + rr * KP + kk, rp + kk);
+      if (has_g) {
+        const double* gp = a.gamma + (row0 + rr) * a.ld_rho;
+        for (int kk = lane; kk < a.k; kk += 32) cp_async8(Gs + rr * KP + kk, gp + kk);
+      }
+      const double* xp = a.x + (row0 + rr) * a.ldx;
+      for (int jj = lane; jj < D; jj += 32) cp_async8(Ys + rr * DP2 + jj, xp + jj);
+      if (a.sw && lane == 0) cp_async8(Ws + rr, a.sw + row0 + rr);
     }
-    // ---- v tile ----
-    for (int e = tid; e < TN * KC; e += nthreads) {
-      const int r = e / KC, kk = e - r * KC;
-      const int64_t row = row0 + r;
-      const int k = k0 + kk;
-      double v = 0.0, va = 0.0, vl = 0.0;
-      if (row < a.n && k < a.k) {
-        va = __ldg(a.rho + row * a.ld_rho + k);
-        if (a.sw) va *= __ldg(a.sw + row);
-        v = va;
-        if (a.gamma) {
-          const double g = __ldg(a.gamma + row * a.ld_rho + k);
-          v = va * g;
-          vl = (va != 0.0) ? va * log(g) : 0.0;   // feeds the dof condition, pmc.pyx:672-679
+  };
+
+  int s = 0;
+  if (int64_t(blockIdx.x) < num_tiles) issue_loads(blockIdx.x, stage0);
+  cp_async_commit();
+
+  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, s ^= 1) {
+    double* st = stage0 + s * stage_len;
+    const int64_t next = tile + gridDim.x;
+    if (next < num_tiles) issue_loads(next, stage0 + (s ^ 1) * stage_len);
+    cp_async_commit();
+    cp_async_wait<1>();            // everything but the group just committed has landed
+    __syncthreads();
+
+    const int64_t row0 = tile * TN;
+    const int rows = int((a.n - row0 < TN) ? (a.n - row0) : TN);
+    double* Vs = st;
+    double* Gs = st + TN * KP;
+    double* Ys = st + TN * KP * (has_g ? 2 : 1);
+    double* Ws = Ys + TN * DP2;
+
+    // ---- in-place transform: v = w rho gamma (zero outside the data), yh = [x - shift, 1, 0] ----
+    double* cs_a = colsum + warp * 2 * KP;                  // this warp's column sums (gamma only)
+    for (int rr = warp; rr < TN; rr += nwarps) {
+      const bool in = rr < rows;
+      const double w = (in && a.sw) ? Ws[rr] : 1.0;
+      for (int kk = lane; kk < KP; kk += 32) {
+        double v = 0.0;
+        if (in && kk < a.k) {
+          v = Vs[rr * KP + kk] * w;
+          if (has_g) {
+            const double g = Gs[rr * KP + kk];
+            cs_a[kk] += v;                                    // same thread every time: ordered, no race
+            cs_a[KP + kk] += (v != 0.0) ? v * log(g) : 0.0;   // feeds the dof condition, pmc.pyx:672-679
+            v *= g;
+          }
         }
+        Vs[rr * KP + kk] = v;
       }
-      vtile[e] = v;
-      if (a.gamma) { atile[e] = va; ltile[e] = vl; }
+      for (int jj = lane; jj < DP2; jj += 32) {
+        double y = 0.0;
+        if (in) y = (jj < D) ? (Ys[rr * DP2 + jj] - shift_s[jj]) : ((jj == D) ? 1.0 : 0.0);
+        Ys[rr * DP2 + jj] = y;
+      }
     }
     __syncthreads();
-    // ---- feature tile ----
-    for (int e = tid; e < TN * FC; e += nthreads) {
-      const int r = e / FC, fl = e - r * FC;
-      const short2 ij = fmap[fl];
-      double p;
-      if (ij.x == -1) p = 1.0;
-      else if (ij.x == -2) p = 0.0;
-      else if (ij.y == -1) p = ytile[r * D + ij.x];
-      else p = ytile[r * D + ij.x] * ytile[r * D + ij.y];
-      phi[e] = p;
-    }
-    __syncthreads();
-    // ---- rank-TN update of the register tiles ----
-    const double* vp = vtile + wkid * K2_TK;
-    const double* pp = phi + wfid * K2_TF + 2 * lane;
+
+    // ---- rank-TN update of the register tile ----
+    const double* vp = Vs + kg * K2_TK;
+    const double* yr = Ys + off_a;
+    const double* yp = Ys + off_b;
 #pragma unroll 2
-    for (int r = 0; r < TN; ++r) {
-      const double2 p0 = *reinterpret_cast<const double2*>(pp + size_t(r) * FC);
-      const double2 p1 = *reinterpret_cast<const double2*>(pp + size_t(r) * FC + 64);
+    for (int n = 0; n < TN; ++n) {
+      const double2 ya = *reinterpret_cast<const double2*>(yr + n * DP2);
+      const double2 yb = *reinterpret_cast<const double2*>(yp + n * DP2);
+      const double f0 = lin ? yb.x : ya.x * yb.x, f1 = lin ? yb.y : ya.x * yb.y;
+      const double f2 = lin ? ya.x : ya.y * yb.x, f3 = lin ? ya.y : ya.y * yb.y;
 #pragma unroll
-      for (int kk = 0; kk < K2_TK / 2; ++kk) {
-        const double2 v = *reinterpret_cast<const double2*>(vp + r * KC + 2 * kk);
-        acc[2 * kk][0] = fma(v.x, p0.x, acc[2 * kk][0]);
-        acc[2 * kk][1] = fma(v.x, p0.y, acc[2 * kk][1]);
-        acc[2 * kk][2] = fma(v.x, p1.x, acc[2 * kk][2]);
-        acc[2 * kk][3] = fma(v.x, p1.y, acc[2 * kk][3]);
-        acc[2 * kk + 1][0] = fma(v.y, p0.x, acc[2 * kk + 1][0]);
-        acc[2 * kk + 1][1] = fma(v.y, p0.y, acc[2 * kk + 1][1]);
-        acc[2 * kk + 1][2] = fma(v.y, p1.x, acc[2 * kk + 1][2]);
-        acc[2 * kk + 1][3] = fma(v.y, p1.y, acc[2 * kk + 1][3]);
+      for (int c = 0; c < K2_TK / 2; ++c) {
+        const double2 v = *reinterpret_cast<const double2*>(vp + n * KP + 2 * c);
+        acc[2 * c][0] = fma(v.x, f0, acc[2 * c][0]);
+        acc[2 * c][1] = fma(v.x, f1, acc[2 * c][1]);
+        acc[2 * c][2] = fma(v.x, f2, acc[2 * c][2]);
+        acc[2 * c][3] = fma(v.x, f3, acc[2 * c][3]);
+        acc[2 * c + 1][0] = fma(v.y, f0, acc[2 * c + 1][0]);
+        acc[2 * c + 1][1] = fma(v.y, f1, acc[2 * c + 1][1]);
+        acc[2 * c + 1][2] = fma(v.y, f2, acc[2 * c + 1][2]);
+        acc[2 * c + 1][3] = fma(v.y, f3, acc[2 * c + 1][3]);
       }
     }
-    if (a.gamma && chunk_f == 0 && tid < KC) {
-      for (int r = 0; r < TN; ++r) { acc_a += atile[r * KC + tid]; acc_l += ltile[r * KC + tid]; }
-    }
+    __syncthreads();   // the stage may be refilled by the loads issued at the top of the next iteration
   }
+  cp_async_wait<0>();
 
   // ---- write this CTA's partial block ----
   const int ldp = a.F + 2;
   double* out = a.partial + size_t(blockIdx.x) * a.k * ldp;
+  if (active) {
 #pragma unroll
-  for (int i = 0; i < K2_TK; ++i) {
-    const int k = k0 + wkid * K2_TK + i;
-    if (k >= a.k) continue;
+    for (int c = 0; c < K2_TK; ++c) {
+      const int k = kg * K2_TK + c;
+      if (k >= a.k) continue;
 #pragma unroll
-    for (int c = 0; c < 2; ++c)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int f = f0 + wfid * K2_TF + 64 * c + 2 * lane + e;
-        if (f < a.F) {
-          out[size_t(k) * ldp + 1 + f] = acc[i][2 * c + e];
-          if (f == 0 && !a.gamma) out[size_t(k) * ldp] = acc[i][2 * c + e];  // A == B without gamma
+      for (int q = 0; q < 4; ++q) {
+        int f;
+        if (lin) {
+          const int j = off_b + q;                    // entry of [y, 1]
+          if (j > D) continue;                        // padding
+          f = (j == D) ? 0 : 1 + j;                   // B_k / m_k
+        } else {
+          const int i = 2 * r + (q >> 1), j = 2 * p + (q & 1);
+          if (j > i || i >= D) continue;              // duplicate above the diagonal / padding (odd D)
+          f = 1 + D + i * (i + 1) / 2 + j;            // second moments, lower triangle row-major
         }
+        out[size_t(k) * ldp + 1 + f] = acc[c][q];
+        if (f == 0 && !has_g) out[size_t(k) * ldp] = acc[c][q];   // A == B without gamma
       }
+    }
   }
-  if (chunk_f == 0 && tid < KC && k0 + tid < a.k) {
-    if (a.gamma) out[size_t(k0 + tid) * ldp] = acc_a;
-    out[size_t(k0 + tid) * ldp + a.F + 1] = acc_l;
+  if (blockIdx.y == 0) {
+    if (has_g) {   // column sums: add the per-warp slots in warp order
+      __syncthreads();
+      for (int k = tid; k < a.k; k += nthreads) {
+        double sa = 0.0, sl = 0.0;
+        for (int wv = 0; wv < nwarps; ++wv) { sa += colsum[wv * 2 * KP + k]; sl += colsum[wv * 2 * KP + KP + k]; }
+        out[size_t(k) * ldp] = sa;
+        out[size_t(k) * ldp + a.F + 1] = sl;
+      }
+    } else {
+      for (int k = tid; k < a.k; k += nthreads) out[size_t(k) * ldp + a.F + 1] = 0.0;
+    }
   }
 }
 

@@ -251,7 +251,7 @@ int pmcb200_suffstats(pmcb200_ctx* c, const double* x, int64_t n, int64_t ldx, i
                       const double* rho, const double* gamma, int k, int ld_rho, const double* weights, double* out,
                       void* stream) {
   PMC_REQUIRE(c != nullptr, "suffstats: NULL context");
-  PMC_REQUIRE(d >= 1 && d <= 181, "suffstats: dimension must be in 1..181");
+  PMC_REQUIRE(d >= 1 && d <= 256, "suffstats: dimension must be in 1..256");
   PMC_REQUIRE(k >= 1 && ld_rho >= k && n >= 0 && ldx >= d, "suffstats: bad sizes");
   PMC_REQUIRE(out != nullptr, "suffstats: NULL output");
   PMC_CUDA_CHECK(cudaSetDevice(c->device));
@@ -266,23 +266,24 @@ int pmcb200_suffstats(pmcb200_ctx* c, const double* x, int64_t n, int64_t ldx, i
   StatsArgs a;
   a.x = x; a.n = n; a.ldx = ldx; a.d = d; a.shift = shift; a.rho = rho; a.gamma = gamma; a.sw = weights;
   a.k = k; a.ld_rho = ld_rho; a.F = F;
-  a.units_k = (k + K2_TK - 1) / K2_TK;
-  a.units_f = (F + K2_TF - 1) / K2_TF;
-  a.wk = std::min(a.units_k, K2_MAX_WARPS);
-  a.wf = std::max(1, std::min(a.units_f, K2_MAX_WARPS / a.wk));
-  const int chunks_k = (a.units_k + a.wk - 1) / a.wk, chunks_f = (a.units_f + a.wf - 1) / a.wf;
-  const int KC = a.wk * K2_TK, FC = a.wf * K2_TF;
-  const size_t per_row = sizeof(double) * (size_t(d) + size_t(KC) * (gamma ? 3 : 1) + FC);
-  const size_t fixed = sizeof(short2) * FC + 64;
-  int tn = int((size_t(200) * 1024 - fixed) / per_row);
-  tn = std::max(2, std::min(64, tn)) & ~1;
+  a.P0 = (d + 1) / 2;
+  a.Bq = a.P0 * (a.P0 + 1) / 2;
+  a.Lq = (d + 4) / 4;
+  a.DP4 = a.Lq * 4;
+  a.KP = ((k + K2_TK - 1) / K2_TK) * K2_TK;
+  a.LT = (a.KP / K2_TK) * (a.Bq + a.Lq);
+  // lane tiles -> CTAs of 8 warps; gy CTAs share the same samples when one CTA cannot hold every tile
+  const int gy = (a.LT + K2_MAX_THREADS - 1) / K2_MAX_THREADS;
+  const int threads = std::min(K2_MAX_THREADS, (((a.LT + gy - 1) / gy + 31) / 32) * 32);
+  const size_t per_row = sizeof(double) * (size_t(a.KP) * (gamma ? 2 : 1) + a.DP4 + 1);
+  const size_t fixed = sizeof(double) * (a.DP4 + (gamma ? size_t(threads / 32) * 2 * a.KP : 0)) + 128;
+  int tn = int((size_t(200) * 1024 - fixed) / (2 * per_row));
+  tn = std::min(128, tn) & ~1;
+  PMC_REQUIRE(tn >= 2, "suffstats: K and D too large for the shared-memory pipeline");
   a.tn = tn;
-  const size_t smem = per_row * tn + fixed + 16;
-  const int nwarps = a.wk * a.wf;
+  const size_t smem = 2 * per_row * tn + fixed;
   const int64_t tiles = (n + tn - 1) / tn;
-  const int ctas_target = c->sm_count * std::max(1, K2_MAX_WARPS / nwarps);
-  const int gy = chunks_k * chunks_f;
-  const int gx = int(std::max<int64_t>(1, std::min<int64_t>(tiles, ctas_target / gy)));
+  const int gx = int(std::max<int64_t>(1, std::min<int64_t>(tiles, std::max(1, c->sm_count / gy))));
   if (int rc = ensure(c->ws, size_t(gx) * len * sizeof(double))) return rc;
   a.partial = static_cast<double*>(c->ws.p);
   static bool attr_set = false;
@@ -290,7 +291,7 @@ int pmcb200_suffstats(pmcb200_ctx* c, const double* x, int64_t n, int64_t ldx, i
     PMC_CUDA_CHECK(cudaFuncSetAttribute(k2_suffstats, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  k2_suffstats<<<dim3(gx, gy), nwarps * 32, smem, st>>>(a);
+  k2_suffstats<<<dim3(gx, gy), threads, smem, st>>>(a);
   PMC_CUDA_CHECK(cudaGetLastError());
   k2_reduce_partials<<<unsigned((len + 255) / 256), 256, 0, st>>>(a.partial, gx, len, out);
   PMC_CUDA_CHECK(cudaGetLastError());
