@@ -24,9 +24,11 @@
 // t = kgroup * (Bq + Lq) + tile (Bq = P0(P0+1)/2 blocks, P0 = ceil(D/2); Lq = ceil((D+1)/4) quads) and dealt to
 // 8 warps per CTA -- two per SM sub-partition, the only warp count that both leaves 255 registers per thread
 // and loads the four schedulers evenly; K=32, D=30 gives exactly 256 lane tiles.  If there are more,
-// gridDim.y CTAs share the same samples.  Samples stream through a two-stage shared-memory pipeline:
-// raw rho / gamma / x / w rows arrive with cp.async (LDGSTS) one tile ahead, a short in-place pass turns them
-// into v and yh, and the block-wide barriers are per 128-sample tile (~37k clk of DFMA work).
+// gridDim.y CTAs share the same samples.  The CTA is warp-specialised: a third warpgroup (setmaxnreg.dec to 88
+// registers, the consumers setmaxnreg.inc to 208) reads rho / gamma / x / w rows from global memory, forms
+// v = w rho gamma and [x - shift, 1] and fills a three-stage shared-memory ring; stages are handed over with
+// mbarriers (full / empty), so the consumers never wait on global memory and there is no block-wide barrier
+// in the sample loop.
 // Each CTA writes one partial block; a second tiny kernel adds the partials in CTA order -- no floating-point
 // atomics, so results are reproducible run to run for a given grid.
 #pragma once
@@ -36,7 +38,6 @@
 namespace pmc {
 
 constexpr int K2_TK = 16;          // components per lane tile
-constexpr int K2_MAX_THREADS = 256;  // 8 warps, two per SM sub-partition
 
 struct StatsArgs {
   const double* x;      // [n, ldx]
@@ -60,31 +61,125 @@ struct StatsArgs {
   double* partial;      // [gridDim.x, k, F+2]   (column 0 = A, column 1+f = Out[k,f], column F+1 = sum w rho ln gamma)
 };
 
-__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+constexpr int K2_CONSUMERS = 256;       // 8 consumer warps (two warpgroups)
+constexpr int K2_PRODUCERS = 128;       // 1 producer warpgroup
+constexpr int K2_THREADS = K2_CONSUMERS + K2_PRODUCERS;
+constexpr int K2_STAGES = 3;
+constexpr int K2_PR = 4;                // rows a producer warp keeps in flight
+// setmaxnreg budget: the CTA owns 384 x 168 = 64512 registers (launch bound); 256 x 208 + 128 x 88 = 64512.
+static_assert(K2_CONSUMERS * 208 + K2_PRODUCERS * 88 <= K2_THREADS * 168, "setmaxnreg.inc would wait forever");
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(K2_MAX_THREADS, 1) k2_suffstats(const StatsArgs a) {
+// Stage layout (doubles): V [TN][KP] | Y [TN][DP4].  The producer warpgroup (88 registers) reads rho / gamma /
+// x / w rows from global memory, forms v = w rho gamma and yh = [x - shift, 1, 0...] and stores them; the two
+// consumer warpgroups (208 registers, setmaxnreg) only ever touch shared memory and the FP64 pipe.
+__global__ void __launch_bounds__(K2_THREADS, 1) k2_suffstats(const StatsArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int tid = threadIdx.x, nthreads = blockDim.x;
-  const int D = a.d, KP = a.KP, DP2 = a.DP4, TN = a.tn;
+  const int tid = threadIdx.x;
+  const int D = a.d, KP = a.KP, DP4 = a.DP4, TN = a.tn;
   const bool has_g = a.gamma != nullptr;
-
-  // stage layout (doubles): V [TN][KP] | G [TN][KP] (gamma only) | Y [TN][DP2] | W [TN]
-  const int stage_len = TN * KP * (has_g ? 2 : 1) + TN * DP2 + TN;
+  const int stage_len = TN * (KP + DP4);
   double* stage0 = reinterpret_cast<double*>(smem_raw);
-  double* shift_s = stage0 + 2 * stage_len;                       // [DP2]
-  double* colsum = shift_s + DP2;                                 // gamma only: [nwarps][2][KP] column sums of w rho, w rho ln(gamma)
-  const int warp = tid >> 5, lane = tid & 31, nwarps = nthreads >> 5;
-  for (int j = tid; j < DP2; j += nthreads) shift_s[j] = (j < D) ? a.shift[j] : 0.0;
-  if (has_g)
-    for (int e = tid; e < nwarps * 2 * KP; e += nthreads) colsum[e] = 0.0;
+  double* shift_s = stage0 + K2_STAGES * stage_len;               // [DP4]
+  double* colsum = shift_s + DP4;                                 // gamma only: [4 producer warps][2][KP]
+  uint64_t* full = reinterpret_cast<uint64_t*>(colsum + (has_g ? 4 * 2 * KP : 0));
+  uint64_t* empty = full + K2_STAGES;
 
+  for (int j = tid; j < DP4; j += K2_THREADS) shift_s[j] = (j < D) ? a.shift[j] : 0.0;
+  if (has_g)
+    for (int e = tid; e < 4 * 2 * KP; e += K2_THREADS) colsum[e] = 0.0;
+  if (tid == 0) {
+    for (int s = 0; s < K2_STAGES; ++s) {
+      mbar_init(&full[s], K2_PRODUCERS);
+      mbar_init(&empty[s], K2_CONSUMERS);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const int64_t num_tiles = (a.n + TN - 1) / TN;
+  const int ldp = a.F + 2;
+  double* out = a.partial + size_t(blockIdx.x) * a.k * ldp;
+
+  if (tid >= K2_CONSUMERS) {
+    // =============================== producer warpgroup ===============================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    const int pw = (tid - K2_CONSUMERS) >> 5, lane = tid & 31;
+    double* cs_a = colsum + pw * 2 * KP;
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int s = it % K2_STAGES;
+      mbar_wait(&empty[s], uint32_t(((it / K2_STAGES) & 1) ^ 1));
+      double* Vs = stage0 + s * stage_len;
+      double* Ys = Vs + TN * KP;
+      const int64_t row0 = tile * TN;
+      const int rows = int((a.n - row0 < TN) ? (a.n - row0) : TN);
+      for (int rb = pw * K2_PR; rb < TN; rb += 4 * K2_PR) {       // K2_PR rows in flight per warp
+        double w[K2_PR];
+#pragma unroll
+        for (int u = 0; u < K2_PR; ++u) w[u] = (a.sw && rb + u < rows) ? __ldg(a.sw + row0 + rb + u) : 1.0;
+        for (int kk = lane; kk < KP; kk += 32) {
+          double rv[K2_PR], gv[K2_PR];
+#pragma unroll
+          for (int u = 0; u < K2_PR; ++u) {
+            const bool in = (rb + u < rows) && (kk < a.k);
+            rv[u] = in ? __ldg(a.rho + (row0 + rb + u) * a.ld_rho + kk) : 0.0;
+            gv[u] = (in && has_g) ? __ldg(a.gamma + (row0 + rb + u) * a.ld_rho + kk) : 1.0;
+          }
+          double sa = 0.0, sl = 0.0;
+#pragma unroll
+          for (int u = 0; u < K2_PR; ++u) {
+            double v = rv[u] * w[u];
+            if (has_g) {
+              sa += v;
+              sl += (v != 0.0) ? v * log(gv[u]) : 0.0;        // feeds the dof condition, pmc.pyx:672-679
+              v *= gv[u];
+            }
+            if (rb + u < TN) Vs[(rb + u) * KP + kk] = v;
+          }
+          if (has_g) { cs_a[kk] += sa; cs_a[KP + kk] += sl; }  // same thread every time: ordered, no race
+        }
+        for (int jj = lane; jj < DP4; jj += 32) {
+          double xv[K2_PR];
+#pragma unroll
+          for (int u = 0; u < K2_PR; ++u)
+            xv[u] = (rb + u < rows && jj < D) ? __ldg(a.x + (row0 + rb + u) * a.ldx + jj) : 0.0;
+          const double sh = shift_s[jj];
+#pragma unroll
+          for (int u = 0; u < K2_PR; ++u) {
+            double y = 0.0;
+            if (rb + u < rows) y = (jj < D) ? (xv[u] - sh) : ((jj == D) ? 1.0 : 0.0);
+            if (rb + u < TN) Ys[(rb + u) * DP4 + jj] = y;
+          }
+        }
+      }
+      mbar_arrive(&full[s]);                                   // release: this thread's stores are visible to waiters
+    }
+    // ---- column sums (gamma) / zero column (no gamma), CTA row 0 only ----
+    if (blockIdx.y == 0) {
+      asm volatile("bar.sync 1, %0;" ::"n"(K2_PRODUCERS) : "memory");   // producers only
+      const int ptid = tid - K2_CONSUMERS;
+      for (int k = ptid; k < a.k; k += K2_PRODUCERS) {
+        if (has_g) {
+          double sa = 0.0, sl = 0.0;
+          for (int wv = 0; wv < 4; ++wv) { sa += colsum[wv * 2 * KP + k]; sl += colsum[wv * 2 * KP + KP + k]; }
+          out[size_t(k) * ldp] = sa;
+          out[size_t(k) * ldp + a.F + 1] = sl;
+        } else {
+          out[size_t(k) * ldp + a.F + 1] = 0.0;
+        }
+      }
+    }
+    return;
+  }
+
+  // ================================= consumer warpgroups =================================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
   // ---- this thread's lane tile ----
-  const int t = blockIdx.y * nthreads + tid;
+  const int t = blockIdx.y * K2_CONSUMERS + tid;
   const bool active = t < a.LT;
   const int tt = active ? t : 0;
   const int per_group = a.Bq + a.Lq;
@@ -106,81 +201,20 @@ __global__ void __launch_bounds__(K2_MAX_THREADS, 1) k2_suffstats(const StatsArg
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
 
-  const int64_t num_tiles = (a.n + TN - 1) / TN;
-
-  auto issue_loads = [&](int64_t tile, double* st) {
-    const int64_t row0 = tile * TN;
-    const int rows = int((a.n - row0 < TN) ? (a.n - row0) : TN);
-    double* Vs = st;
-    double* Gs = st + TN * KP;
-    double* Ys = st + TN * KP * (has_g ? 2 : 1);
-    double* Ws = Ys + TN * DP2;
-    for (int rr = warp; rr < rows; rr += nwarps) {          // one warp per sample row, lanes over columns
-      const double* rp = a.rho + (row0 + rr) * a.ld_rho;
-      for (int kk = lane; kk < a.k; kk += 32) cp_async8(Vs + rr * KP + kk, rp + kk);
-      if (has_g) {
-        const double* gp = a.gamma + (row0 + rr) * a.ld_rho;
-        for (int kk = lane; kk < a.k; kk += 32) cp_async8(Gs + rr * KP + kk, gp + kk);
-      }
-      const double* xp = a.x + (row0 + rr) * a.ldx;
-      for (int jj = lane; jj < D; jj += 32) cp_async8(Ys + rr * DP2 + jj, xp + jj);
-      if (a.sw && lane == 0) cp_async8(Ws + rr, a.sw + row0 + rr);
-    }
-  };
-
-  int s = 0;
-  if (int64_t(blockIdx.x) < num_tiles) issue_loads(blockIdx.x, stage0);
-  cp_async_commit();
-
-  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, s ^= 1) {
-    double* st = stage0 + s * stage_len;
-    const int64_t next = tile + gridDim.x;
-    if (next < num_tiles) issue_loads(next, stage0 + (s ^ 1) * stage_len);
-    cp_async_commit();
-    cp_async_wait<1>();            // everything but the group just committed has landed
-    __syncthreads();
-
-    const int64_t row0 = tile * TN;
-    const int rows = int((a.n - row0 < TN) ? (a.n - row0) : TN);
-    double* Vs = st;
-    double* Gs = st + TN * KP;
-    double* Ys = st + TN * KP * (has_g ? 2 : 1);
-    double* Ws = Ys + TN * DP2;
-
-    // ---- in-place transform: v = w rho gamma (zero outside the data), yh = [x - shift, 1, 0] ----
-    double* cs_a = colsum + warp * 2 * KP;                  // this warp's column sums (gamma only)
-    for (int rr = warp; rr < TN; rr += nwarps) {
-      const bool in = rr < rows;
-      const double w = (in && a.sw) ? Ws[rr] : 1.0;
-      for (int kk = lane; kk < KP; kk += 32) {
-        double v = 0.0;
-        if (in && kk < a.k) {
-          v = Vs[rr * KP + kk] * w;
-          if (has_g) {
-            const double g = Gs[rr * KP + kk];
-            cs_a[kk] += v;                                    // same thread every time: ordered, no race
-            cs_a[KP + kk] += (v != 0.0) ? v * log(g) : 0.0;   // feeds the dof condition, pmc.pyx:672-679
-            v *= g;
-          }
-        }
-        Vs[rr * KP + kk] = v;
-      }
-      for (int jj = lane; jj < DP2; jj += 32) {
-        double y = 0.0;
-        if (in) y = (jj < D) ? (Ys[rr * DP2 + jj] - shift_s[jj]) : ((jj == D) ? 1.0 : 0.0);
-        Ys[rr * DP2 + jj] = y;
-      }
-    }
-    __syncthreads();
-
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    const int s = it % K2_STAGES;
+    mbar_wait(&full[s], uint32_t((it / K2_STAGES) & 1));
+    const double* Vs = stage0 + s * stage_len;
+    const double* Ys = Vs + TN * KP;
     // ---- rank-TN update of the register tile ----
     const double* vp = Vs + kg * K2_TK;
     const double* yr = Ys + off_a;
     const double* yp = Ys + off_b;
 #pragma unroll 2
     for (int n = 0; n < TN; ++n) {
-      const double2 ya = *reinterpret_cast<const double2*>(yr + n * DP2);
-      const double2 yb = *reinterpret_cast<const double2*>(yp + n * DP2);
+      const double2 ya = *reinterpret_cast<const double2*>(yr + n * DP4);
+      const double2 yb = *reinterpret_cast<const double2*>(yp + n * DP4);
       const double f0 = lin ? yb.x : ya.x * yb.x, f1 = lin ? yb.y : ya.x * yb.y;
       const double f2 = lin ? ya.x : ya.y * yb.x, f3 = lin ? ya.y : ya.y * yb.y;
 #pragma unroll
@@ -196,13 +230,10 @@ __global__ void __launch_bounds__(K2_MAX_THREADS, 1) k2_suffstats(const StatsArg
         acc[2 * c + 1][3] = fma(v.y, f3, acc[2 * c + 1][3]);
       }
     }
-    __syncthreads();   // the stage may be refilled by the loads issued at the top of the next iteration
+    mbar_arrive(&empty[s]);                                     // the producer may refill this stage
   }
-  cp_async_wait<0>();
 
   // ---- write this CTA's partial block ----
-  const int ldp = a.F + 2;
-  double* out = a.partial + size_t(blockIdx.x) * a.k * ldp;
   if (active) {
 #pragma unroll
     for (int c = 0; c < K2_TK; ++c) {
@@ -223,19 +254,6 @@ __global__ void __launch_bounds__(K2_MAX_THREADS, 1) k2_suffstats(const StatsArg
         out[size_t(k) * ldp + 1 + f] = acc[c][q];
         if (f == 0 && !has_g) out[size_t(k) * ldp] = acc[c][q];   // A == B without gamma
       }
-    }
-  }
-  if (blockIdx.y == 0) {
-    if (has_g) {   // column sums: add the per-warp slots in warp order
-      __syncthreads();
-      for (int k = tid; k < a.k; k += nthreads) {
-        double sa = 0.0, sl = 0.0;
-        for (int wv = 0; wv < nwarps; ++wv) { sa += colsum[wv * 2 * KP + k]; sl += colsum[wv * 2 * KP + KP + k]; }
-        out[size_t(k) * ldp] = sa;
-        out[size_t(k) * ldp + a.F + 1] = sl;
-      }
-    } else {
-      for (int k = tid; k < a.k; k += nthreads) out[size_t(k) * ldp + a.F + 1] = 0.0;
     }
   }
 }

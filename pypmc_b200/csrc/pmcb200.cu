@@ -272,16 +272,15 @@ int pmcb200_suffstats(pmcb200_ctx* c, const double* x, int64_t n, int64_t ldx, i
   a.DP4 = a.Lq * 4;
   a.KP = ((k + K2_TK - 1) / K2_TK) * K2_TK;
   a.LT = (a.KP / K2_TK) * (a.Bq + a.Lq);
-  // lane tiles -> CTAs of 8 warps; gy CTAs share the same samples when one CTA cannot hold every tile
-  const int gy = (a.LT + K2_MAX_THREADS - 1) / K2_MAX_THREADS;
-  const int threads = std::min(K2_MAX_THREADS, (((a.LT + gy - 1) / gy + 31) / 32) * 32);
-  const size_t per_row = sizeof(double) * (size_t(a.KP) * (gamma ? 2 : 1) + a.DP4 + 1);
-  const size_t fixed = sizeof(double) * (a.DP4 + (gamma ? size_t(threads / 32) * 2 * a.KP : 0)) + 128;
-  int tn = int((size_t(200) * 1024 - fixed) / (2 * per_row));
-  tn = std::min(128, tn) & ~1;
-  PMC_REQUIRE(tn >= 2, "suffstats: K and D too large for the shared-memory pipeline");
+  // lane tiles -> CTAs of 8 consumer warps; gy CTAs share the same samples when one CTA cannot hold every tile
+  const int gy = (a.LT + K2_CONSUMERS - 1) / K2_CONSUMERS;
+  const size_t per_row = sizeof(double) * (size_t(a.KP) + a.DP4);
+  const size_t fixed = sizeof(double) * (a.DP4 + (gamma ? size_t(8) * a.KP : 0)) + 2 * K2_STAGES * sizeof(uint64_t) + 128;
+  int tn = int((size_t(210) * 1024 - fixed) / (K2_STAGES * per_row));
+  tn = std::min(96, tn) & ~7;
+  PMC_REQUIRE(tn >= 8, "suffstats: K and D too large for the shared-memory pipeline");
   a.tn = tn;
-  const size_t smem = 2 * per_row * tn + fixed;
+  const size_t smem = K2_STAGES * per_row * tn + fixed;
   const int64_t tiles = (n + tn - 1) / tn;
   const int gx = int(std::max<int64_t>(1, std::min<int64_t>(tiles, std::max(1, c->sm_count / gy))));
   if (int rc = ensure(c->ws, size_t(gx) * len * sizeof(double))) return rc;
@@ -291,7 +290,7 @@ int pmcb200_suffstats(pmcb200_ctx* c, const double* x, int64_t n, int64_t ldx, i
     PMC_CUDA_CHECK(cudaFuncSetAttribute(k2_suffstats, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  k2_suffstats<<<dim3(gx, gy), threads, smem, st>>>(a);
+  k2_suffstats<<<dim3(gx, gy), K2_THREADS, smem, st>>>(a);
   PMC_CUDA_CHECK(cudaGetLastError());
   k2_reduce_partials<<<unsigned((len + 255) / 256), 256, 0, st>>>(a.partial, gx, len, out);
   PMC_CUDA_CHECK(cudaGetLastError());
