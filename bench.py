@@ -78,7 +78,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -87,9 +87,11 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summarise the samples that arrived in [t0, t1] (the timed region); if fewer than 3 did, all samples
+        since start() (warm-up + timed region, the same load) are used and ``window`` says so."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -99,7 +101,11 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        inside = [ln for (t, ln) in self.lines if t0 is not None and t0 <= t <= t1 + 0.03]
+        window = "timed region"
+        if len(inside) < 3:
+            inside, window = [ln for (_, ln) in self.lines], "warm-up + timed region"
+        for ln in inside:
             f = [c.strip() for c in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -111,7 +117,8 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "window": window,
+                "reasons": sorted(reasons)}
 
 
 def measured_peaks():
@@ -139,12 +146,14 @@ def cpu_reference_pass(x, comps, weights, threads):
         return np.concatenate(list(ex.map(work, range(threads))))
 
 
-def cpu_arm(rows, steps, warmup, threads):
+def cpu_arm(rows, steps, warmup, threads, x=None):
     from oracle import oracle as orc
     orc.build()
     means, covs, w = synth_mixture()
     comps = orc.Components(means, covs)
-    x = synth_samples_host(rows, means, covs)
+    if x is None:
+        x = synth_samples_host(rows, means, covs)
+    x = x[:rows]
     for _ in range(warmup):
         cpu_reference_pass(x, comps, w, threads)
     t0 = time.perf_counter()
@@ -159,7 +168,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    rows = int(min(N_PER_GPU, 40_000 * threads))
+    rows = int(min(N_PER_GPU, 125_000 * threads))          # ~1 s of CPU work per step on this pool's hosts
     value, dt = cpu_arm(rows, args.steps, args.warmup, threads)
     sample = "%d of %d rows per step (bounded sample of the same workload), oracle/pmc_oracle.c over %d threads" % (
         rows, N_PER_GPU, threads)
@@ -208,24 +217,27 @@ def run_gpu(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    sync_all()
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+        time.sleep(0.3)                                    # let nvidia-smi come up before the load starts
+    for _ in range(args.warmup):
+        step()
+    sync_all()
     launches0 = ctx.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     sync_all()
+    t_begin = time.time()
     ev[0].record()
     for i in range(args.steps):
         step()
         ev[i + 1].record()
     sync_all()
+    t_end = time.time()
     launches = ctx.launch_count() - launches0
     total_ms = ev[0].elapsed_time(ev[-1])
     per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop(t_begin, t_end) if rank == 0 else None
     t_ms = torch.tensor([total_ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
@@ -258,29 +270,44 @@ def run_gpu(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline: the binding roof is the FP64 FMA pipe, measured live; HBM fraction reported beside it
+    # ---- roofline: the binding roof is the FP64 FMA pipe, measured live; HBM fraction reported beside it.
+    # The timed region is short (steps x ~13 ms), so the burst DFMA figure is the denominator; a 2 s DFMA run
+    # (sustained, power/thermal steady state) is reported next to it.
     peak_gflops, _ = ctx.fp64_peak(0, 3000)
-    kernel_ms = float(np.median(per_step))                # K1 is the only kernel of a step
+    sustained_gflops, sustained_ms = ctx.fp64_peak(0, 250000)
+    kernel_ms = float(np.median(per_step))                # prepare + K1 (the exact-difference form returns at once)
     flops = FLOP_PER_PAIR * float(n) * K
     achieved_tf = flops / (kernel_ms * 1e-3) * 1e-12
     peaks, peak_src = measured_peaks()
     hbm_bytes = BYTES_PER_SAMPLE * float(n)
     hbm_gbs = hbm_bytes / (kernel_ms * 1e-3) * 1e-9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "k1_ncu_traffic.json")   # dram bytes per launch from the committed ncu capture
+    if os.path.exists(tpath):
+        with open(tpath) as fh:
+            tj = json.load(fh)
+        if tj.get("rows") == n:
+            traffic = tj.get("dram_bytes_per_launch")
     roofline = {
         "bound": "fp64", "achieved": achieved_tf, "peak": peak_gflops * 1e-3, "unit": "TFLOP/s",
-        "frac": achieved_tf / (peak_gflops * 1e-3), "traffic": None,
-        "peak_source": "DFMA microbenchmark run in this process (pmcb200_fp64_peak, register-resident chains, burst)",
-        "kernel": "k1_mixture_eval<30>", "kernel_ms": kernel_ms, "algorithmic_flops_per_launch": flops,
+        "frac": achieved_tf / (peak_gflops * 1e-3), "traffic": traffic,
+        "peak_source": "measured: DFMA microbenchmark run in this process (pmcb200_fp64_peak, register-resident "
+                       "chains on every SM, burst); MEASURED_PEAKS.json has no FP64 entry",
+        "peak_sustained": sustained_gflops * 1e-3, "peak_sustained_ms": sustained_ms,
+        "kernel": "k1_fast_eval<30>", "kernel_ms": kernel_ms, "algorithmic_flops_per_launch": flops,
         "hbm": {"achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_gbs / peaks["hbm_gbs"],
                 "algorithmic_bytes_per_launch": hbm_bytes, "peak_source": peak_src},
     }
 
-    # ---- CPU baseline: the oracle (port of the reference algorithm) on a bounded sample, all host threads
+    # ---- CPU baseline: the oracle (port of the reference algorithm) on a bounded sample, all host threads.
+    # A 200k-row probe sizes the sample to ~15 s of CPU work (at most the whole workload).
     threads = os.cpu_count() or 1
-    cpu_rows = int(min(n, 40_000 * threads))
-    cpu_value, cpu_dt = cpu_arm(cpu_rows, 1, 1, threads)
+    probe_rows = int(min(e2e_rows, 200_000))
+    probe_value, _ = cpu_arm(probe_rows, 1, 1, threads, x=xh)
+    cpu_rows = int(min(e2e_rows, max(probe_rows, 15.0 * probe_value / K)))
+    cpu_value, cpu_dt = cpu_arm(cpu_rows, 1, 0, threads, x=xh)
     cpu = {"value": cpu_value, "unit": "pairs/s", "cores": threads, "kind": "port",
-           "sample": "%d of %d rows, 1 warm-up + 1 timed pass (%.1f s), oracle/pmc_oracle.c over %d threads"
+           "sample": "first %d of %d rows of the same workload, 1 timed pass (%.1f s), oracle/pmc_oracle.c over %d threads"
                      % (cpu_rows, n, cpu_dt, threads)}
 
     print(json.dumps({
@@ -303,7 +330,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=0, help="samples per GPU (default 1e7, the BASELINE config)")
