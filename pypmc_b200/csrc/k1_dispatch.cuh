@@ -12,6 +12,7 @@ struct K1Launch {
   const double* derived;    // records with the centre slot replaced by -b (k1_prepare)
   const double* shift;      // [DP]
   const int* flag;
+  double* rowstat;          // [n, 2] for k1_finish, or null
 };
 
 // returns cudaError_t as int; grid <= #SMs (persistent CTAs, one per SM)
@@ -37,7 +38,7 @@ int k1_tile_rows(int dp);   // samples per CTA tile for this DP (same for both f
       if (e != cudaSuccess) return int(e);                                                            \
       attr_set = true;                                                                                \
     }                                                                                                 \
-    FastArgs fa{l.base, l.shift, l.flag};                                                             \
+    FastArgs fa{l.base, l.shift, l.flag, l.rowstat};                                                          \
     fa.e.records = l.derived;                                                                         \
     const bool staged = l.base.lp_out || l.base.resp_out || l.base.aux_out;                           \
     const size_t smem = (staged ? FastCfg<DP>::SMEM_STAGED : FastCfg<DP>::SMEM_BASE) + 16;            \

@@ -26,7 +26,9 @@
 //
 // N x K outputs: log-pdfs are staged per warp in shared memory ([KC components][rows], conflict-free) and
 // written row-major with lanes running over components, so the global stores are full 32-byte sectors;
-// the second pass (rho = exp(lp) w_k / (exp(log q) + tiny), or the VB soft-max) re-reads them the same way.
+// the second pass (rho = exp(lp) w_k / (exp(log q) + tiny), or the VB soft-max) is a separate streaming kernel
+// (k1_finish, k1_prepare.cuh) that runs at HBM speed; inside this kernel it cost 3.5 ms of 16.4 at C2 and
+// 14 ms of 27 at C3 because its dependent load -> exp -> store chains had only two warps per scheduler to hide behind.
 #pragma once
 
 #include "k1_mixture_eval.cuh"
@@ -39,6 +41,7 @@ struct FastArgs {
   EvalArgs e;             // e.records = derived records (centre slot holds -b_k)
   const double* shift;    // [DP] c
   const int* flag;        // 0: fast form runs; 1: exact-difference form runs
+  double* rowstat;        // [n, 2] per-row (running max, 1/denominator) for k1_finish, or null when no second pass follows
 };
 
 template <int DP>
@@ -101,9 +104,7 @@ __global__ void __launch_bounds__(FastCfg<DP>::NW * 32, 1) k1_fast_eval(const Fa
 
   double part_a = 0.0, part_w = 0.0;
   double* const scratch = a.lp_out ? a.lp_out : a.resp_out;
-  const bool second_pass = (a.resp_out != nullptr) || (a.mode == MODE_VB && a.lp_out != nullptr);
   const bool vec_ok = (a.d == DP) && ((a.ldx & 1) == 0) && ((reinterpret_cast<uintptr_t>(a.x) & 15) == 0);
-  const int hw = (a.kl > 16) ? 32 : (a.kl > 8) ? 16 : (a.kl > 4) ? 8 : 4;   // lanes per row in pass 2
 
   int64_t step = 0;
   for (int64_t it = 0; it < my_tiles; ++it) {
@@ -255,62 +256,20 @@ __global__ void __launch_bounds__(FastCfg<DP>::NW * 32, 1) k1_fast_eval(const Fa
     }
 
     // ---- per-sample results ----
-    double lq[S], dinv[S];
 #pragma unroll
     for (int s = 0; s < S; ++s) {
       const int64_t row = row0 + lane + 32 * s;
-      lq[s] = log(run_sum[s]) + run_max[s];                       // _regularize.pyx:81
-      dinv[s] = 0.0;
-      if (row < a.n) {
-        const double w_n = a.sw ? __ldg(a.sw + row) : 1.0;
-        part_w += w_n;
-        if (a.logq) a.logq[row] = lq[s];
-        if (a.mode != MODE_VB) {
-          part_a += w_n * lq[s];                                  // pmc.pyx:388-391
-          dinv[s] = 1.0 / (exp(lq[s]) + kTiny);                   // pmc.pyx:39-41
-        } else {
-          dinv[s] = 1.0 / run_sum[s];                             // variational.pyx:728-755
-        }
+      if (row >= a.n) continue;
+      const double lq = log(run_sum[s]) + run_max[s];             // _regularize.pyx:81
+      const double w_n = a.sw ? __ldg(a.sw + row) : 1.0;
+      part_w += w_n;
+      if (a.logq) a.logq[row] = lq;
+      if (a.mode != MODE_VB) part_a += w_n * lq;                  // pmc.pyx:388-391
+      if (fa.rowstat) {
+        fa.rowstat[2 * row] = run_max[s];
+        fa.rowstat[2 * row + 1] = (a.mode != MODE_VB) ? 1.0 / (exp(lq) + kTiny)   // pmc.pyx:39-41
+                                                      : 1.0 / run_sum[s];         // variational.pyx:728-755
       }
-    }
-
-    // ---- pass 2 (responsibilities), row-major: lanes run over the evaluated components ----
-    if (second_pass) {
-      __syncwarp();   // the flushes above must be visible to the whole warp (global memory, same warp)
-      __threadfence_block();
-      double acc = 0.0;
-      const int per = 32 / hw;                                    // rows handled per instruction
-      const int l_k = lane % hw, l_r = lane / hw;
-      for (int kb = 0; kb < a.kl; kb += hw) {
-        const int kk = kb + l_k;
-        const bool live = kk < a.kl;
-        const int col = live ? __ldg(a.cols + kk) : 0;
-        const double wk = live ? a.records[size_t(kk) * RL + NT + DP + S_WEIGHT] : 0.0;
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-          for (int rr = 0; rr < 32; rr += per) {
-            const int src = rr + l_r;                             // lane that owns this row's scalars
-            const double d_r = __shfl_sync(0xffffffffu, dinv[s], src);
-            const double m_r = __shfl_sync(0xffffffffu, run_max[s], src);
-            const int64_t row = row0 + 32 * s + src;
-            if (!live || row >= a.n) continue;
-            const size_t o = size_t(row) * a.k_out + col;
-            if (a.mode != MODE_VB) {
-              a.resp_out[o] = exp(scratch[o]) * wk * d_r;         // pmc.pyx:39-41
-            } else {
-              const double lr = scratch[o] - m_r;
-              double rv = exp(lr) * d_r;
-              if (rv == 0.0) rv = kTiny;                          // variational.pyx:753-754
-              const double lrn = lr + log(d_r);
-              if (a.resp_out) a.resp_out[o] = rv;
-              if (a.lp_out) a.lp_out[o] = lrn;
-              const double w_r = a.sw ? __ldg(a.sw + row) : 1.0;
-              acc = fma(w_r * rv, lrn, acc);                      // variational.pyx:1003-1013
-            }
-          }
-        }
-      }
-      part_a += acc;
     }
   }
 

@@ -50,4 +50,96 @@ __global__ void __launch_bounds__(256, 1) k1_prepare(const double* __restrict__ 
   if (threadIdx.x == 0) *flag = bad;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// k1_finish: second pass of K1 as a streaming kernel (runs iff the fast form did, *flag == 0).
+//   mixture modes : rho_nk = exp(lp_nk) w_k / (exp(log q_n) + tiny)                 pmc.pyx:39-41
+//   VB mode       : r_nk = exp(lp - max) / norm (zeros -> tiny), log_rho <- lp - max + ln(1/norm),
+//                   partial sums of w_n r_nk log r_nk                               variational.pyx:728-755, 1003-1013
+// `scratch` holds lp_nk (written row-major by k1_fast_eval), rowstat the per-row (max, 1/denominator).
+// A warp covers 32/hw rows per step with hw lanes running over the evaluated components (coalesced),
+// four steps in flight.  Per-block partial sums are written in block order (deterministic).
+// ---------------------------------------------------------------------------------------------
+struct FinishArgs {
+  int64_t n;
+  int kl, k_out, mode, rl, w_off;   // record length and offset of the weight scalar inside a record
+  const double* records;
+  const int* cols;
+  const double* rowstat;
+  const double* sw;
+  double* scratch;
+  double* lp_out;
+  double* resp_out;
+  const int* flag;
+  double* fin_partials;             // [gridDim.x] or null
+};
+
+__global__ void __launch_bounds__(256, 4) k1_finish(const FinishArgs a) {
+  if (*a.flag != 0) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int hw = (a.kl > 16) ? 32 : (a.kl > 8) ? 16 : (a.kl > 4) ? 8 : 4;
+  const int per = 32 / hw, l_k = lane % hw, l_r = lane / hw;
+  constexpr int U = 4;
+  const int64_t rows_per_step = int64_t(per) * U;
+  const int64_t gwarp = int64_t(blockIdx.x) * (blockDim.x >> 5) + warp, nwarps = int64_t(gridDim.x) * (blockDim.x >> 5);
+  double acc = 0.0;
+  for (int kb = 0; kb < a.kl; kb += hw) {
+    const int kk = kb + l_k;
+    const bool live = kk < a.kl;
+    const int col = live ? __ldg(a.cols + kk) : 0;
+    const double wk = live ? __ldg(a.records + size_t(kk) * a.rl + a.w_off) : 0.0;
+    for (int64_t r0 = gwarp * rows_per_step; r0 < a.n; r0 += nwarps * rows_per_step) {
+      double lpv[U], mx[U], dv[U];
+      bool ok[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t row = r0 + u * per + l_r;
+        ok[u] = live && row < a.n;
+        lpv[u] = ok[u] ? a.scratch[size_t(row) * a.k_out + col] : 0.0;
+        mx[u] = ok[u] ? __ldg(a.rowstat + 2 * row) : 0.0;
+        dv[u] = ok[u] ? __ldg(a.rowstat + 2 * row + 1) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (!ok[u]) continue;
+        const int64_t row = r0 + u * per + l_r;
+        const size_t o = size_t(row) * a.k_out + col;
+        if (a.mode != MODE_VB) {
+          a.resp_out[o] = exp(lpv[u]) * wk * dv[u];
+        } else {
+          const double lr = lpv[u] - mx[u];
+          double rv = exp(lr) * dv[u];
+          if (rv == 0.0) rv = kTiny;
+          const double lrn = lr + log(dv[u]);
+          if (a.resp_out) a.resp_out[o] = rv;
+          if (a.lp_out) a.lp_out[o] = lrn;
+          const double w_r = a.sw ? __ldg(a.sw + row) : 1.0;
+          acc = fma(w_r * rv, lrn, acc);
+        }
+      }
+    }
+  }
+  if (a.fin_partials) {
+    __shared__ double red[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int w = 0; w < int(blockDim.x >> 5); ++w) s += red[w];
+      a.fin_partials[blockIdx.x] = s;
+    }
+  }
+}
+
+// sums[0] += sum_b fin_partials[b] in block order (VB: sum_n w_n sum_k r log r)
+__global__ void k1_reduce_finish(const double* __restrict__ fin_partials, int count, const int* __restrict__ flag,
+                                 double* __restrict__ sums) {
+  if (*flag != 0 || threadIdx.x != 0) return;
+  double s = 0.0;
+  for (int i = 0; i < count; ++i) s += fin_partials[i];
+  sums[0] += s;
+}
+
 }  // namespace pmc

@@ -85,9 +85,10 @@ struct pmcb200_ctx {
   int sm_count = 0;
   DevBuf ws;              // partial sums of K2 / microbenchmark scratch
   DevBuf k1ws;            // K1: derived records, shift, flag, per-warp partial sums (device-pointer entry point)
+  DevBuf k1row;           // K1: per-row (max, 1/denominator) handed from k1_fast_eval to k1_finish
   cudaStream_t copy_stream[2] = {nullptr, nullptr};
   // host pipeline: per-slot device buffers
-  DevBuf hx[2], hw[2], hlogq[2], hlp[2], hresp[2], haux[2], hws[2], hsums[2];
+  DevBuf hx[2], hw[2], hlogq[2], hlp[2], hresp[2], haux[2], hws[2], hsums[2], hrow[2];
   DevBuf hrec, hcols;
   int64_t launches = 0;
 };
@@ -137,11 +138,11 @@ int pmcb200_create(int device, pmcb200_ctx** out) {
 int pmcb200_destroy(pmcb200_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
-  DevBuf* all[] = {&c->ws, &c->k1ws, &c->hrec, &c->hcols};
+  DevBuf* all[] = {&c->ws, &c->k1ws, &c->k1row, &c->hrec, &c->hcols};
   for (DevBuf* b : all)
     if (b->p) cudaFree(b->p);
   for (int i = 0; i < 2; ++i) {
-    DevBuf* slot[] = {&c->hx[i], &c->hw[i], &c->hlogq[i], &c->hlp[i], &c->hresp[i], &c->haux[i], &c->hws[i], &c->hsums[i]};
+    DevBuf* slot[] = {&c->hx[i], &c->hw[i], &c->hlogq[i], &c->hlp[i], &c->hresp[i], &c->haux[i], &c->hws[i], &c->hsums[i], &c->hrow[i]};
     for (DevBuf* b : slot)
       if (b->p) cudaFree(b->p);
     if (c->copy_stream[i]) cudaStreamDestroy(c->copy_stream[i]);
@@ -191,7 +192,8 @@ static int eval_prepare(pmcb200_ctx* c, DevBuf& prep, const EvalArgs& a, cudaStr
   const int rl = record_len(dp);
   const size_t n_part = size_t(c->sm_count) * PMC_MAX_WARPS * 2;
   const size_t off_shift = size_t(a.kl) * rl, off_part = off_shift + PMC_MAX_DP, off_flag = off_part + n_part;
-  if (int rc = ensure(prep, (off_flag + 2) * sizeof(double))) return rc;
+  const size_t off_fin = off_flag + 2, n_fin = size_t(c->sm_count) * 8;
+  if (int rc = ensure(prep, (off_fin + n_fin) * sizeof(double))) return rc;
   double* base = static_cast<double*>(prep.p);
   k1_prepare<<<1, 256, 0, st>>>(a.records, a.kl, dp, base, base + off_shift, reinterpret_cast<int*>(base + off_flag),
                                 base + off_part, int(n_part));
@@ -202,14 +204,23 @@ static int eval_prepare(pmcb200_ctx* c, DevBuf& prep, const EvalArgs& a, cudaStr
   out->flag = reinterpret_cast<int*>(base + off_flag);
   out->base = a;
   out->base.partials = base + off_part;
+  out->rowstat = base + off_fin;       // (re-used as the pointer to the finish kernel's per-block partial sums)
   return 0;
 }
 
-static int eval_launch(pmcb200_ctx* c, const K1Launch& prep, const EvalArgs& a0, double* sums_dev, cudaStream_t st) {
-  K1Launch l = prep;
+static int eval_launch(pmcb200_ctx* c, const K1Launch& prep, DevBuf& rowbuf, const EvalArgs& a0, double* sums_dev,
+                       cudaStream_t st) {
+  K1Launch l = prep;   // derived / shift / flag of the prepared records
   double* partials = prep.base.partials;
+  double* fin_partials = prep.rowstat;
   l.base = a0;
   l.base.partials = sums_dev ? partials : nullptr;
+  const bool second_pass = (a0.resp_out != nullptr) || (a0.mode == MODE_VB && a0.lp_out != nullptr);
+  l.rowstat = nullptr;
+  if (second_pass) {
+    if (int rc = ensure(rowbuf, size_t(a0.n) * 2 * sizeof(double))) return rc;
+    l.rowstat = static_cast<double*>(rowbuf.p);
+  }
   const int dp = (a0.d + 1) & ~1;
   const int ts = k1_tile_rows(dp);
   const int64_t tiles = (a0.n + ts - 1) / ts;
@@ -220,11 +231,29 @@ static int eval_launch(pmcb200_ctx* c, const K1Launch& prep, const EvalArgs& a0,
     return 1;
   }
   c->launches += 2;
+  const int fin_grid = c->sm_count * 8;
+  const bool fin_sum = second_pass && sums_dev && a0.mode == MODE_VB;
+  if (second_pass) {
+    FinishArgs f;
+    f.n = a0.n; f.kl = a0.kl; f.k_out = a0.k_out; f.mode = a0.mode;
+    f.rl = record_len(dp); f.w_off = tri_len(dp) + dp + S_WEIGHT;
+    f.records = l.derived; f.cols = a0.cols; f.rowstat = l.rowstat; f.sw = a0.sw;
+    f.scratch = a0.lp_out ? a0.lp_out : a0.resp_out; f.lp_out = a0.lp_out; f.resp_out = a0.resp_out;
+    f.flag = l.flag; f.fin_partials = fin_sum ? fin_partials : nullptr;
+    k1_finish<<<fin_grid, 256, 0, st>>>(f);
+    PMC_CUDA_CHECK(cudaGetLastError());
+    c->launches++;
+  }
   if (sums_dev) {
     // partial slots of CTAs / warps that did not run hold the zeros written by k1_prepare (or by the last reduce)
     k1_reduce_sums<<<1, 32, 0, st>>>(partials, c->sm_count * PMC_MAX_WARPS, sums_dev);
     PMC_CUDA_CHECK(cudaGetLastError());
     c->launches++;
+    if (fin_sum) {
+      k1_reduce_finish<<<1, 32, 0, st>>>(fin_partials, fin_grid, l.flag, sums_dev);
+      PMC_CUDA_CHECK(cudaGetLastError());
+      c->launches++;
+    }
   }
   return 0;
 }
@@ -244,7 +273,7 @@ int pmcb200_mixture_eval(pmcb200_ctx* c, const double* x, int64_t n, int64_t ldx
   EvalArgs a{x, n, ldx, d, records, cols, kl, k_out, mode, max_init, logq, lp, resp, aux, weights, nullptr, nullptr};
   K1Launch prep;
   if (int rc = eval_prepare(c, c->k1ws, a, st, &prep)) return rc;
-  return eval_launch(c, prep, a, sums, st);
+  return eval_launch(c, prep, c->k1row, a, sums, st);
 }
 
 int pmcb200_suffstats(pmcb200_ctx* c, const double* x, int64_t n, int64_t ldx, int d, const double* shift,
@@ -362,7 +391,7 @@ int pmcb200_mixture_eval_host(pmcb200_ctx* c, const double* x, int64_t n, int64_
                resp ? static_cast<double*>(c->hresp[s].p) : nullptr,
                aux ? static_cast<double*>(c->haux[s].p) : nullptr,
                weights ? static_cast<const double*>(c->hw[s].p) : nullptr, nullptr, nullptr};
-    if (int rc = eval_launch(c, prep[s], a, sums ? static_cast<double*>(c->hsums[s].p) : nullptr, st)) return rc;
+    if (int rc = eval_launch(c, prep[s], c->hrow[s], a, sums ? static_cast<double*>(c->hsums[s].p) : nullptr, st)) return rc;
     if (logq) PMC_CUDA_CHECK(cudaMemcpyAsync(logq + r0, c->hlogq[s].p, size_t(rows) * sizeof(double), cudaMemcpyDeviceToHost, st));
     const size_t out_bytes = size_t(rows) * k_out * sizeof(double);
     if (lp) PMC_CUDA_CHECK(cudaMemcpyAsync(lp + r0 * k_out, c->hlp[s].p, out_bytes, cudaMemcpyDeviceToHost, st));
