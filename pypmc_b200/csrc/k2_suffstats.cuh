@@ -117,42 +117,91 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_suffstats(const StatsArgs a)
       double* Ys = Vs + TN * KP;
       const int64_t row0 = tile * TN;
       const int rows = int((a.n - row0 < TN) ? (a.n - row0) : TN);
-      for (int rb = pw * K2_PR; rb < TN; rb += 4 * K2_PR) {       // K2_PR rows in flight per warp
-        double w[K2_PR];
-#pragma unroll
-        for (int u = 0; u < K2_PR; ++u) w[u] = (a.sw && rb + u < rows) ? __ldg(a.sw + row0 + rb + u) : 1.0;
-        for (int kk = lane; kk < KP; kk += 32) {
-          double rv[K2_PR], gv[K2_PR];
-#pragma unroll
-          for (int u = 0; u < K2_PR; ++u) {
-            const bool in = (rb + u < rows) && (kk < a.k);
-            rv[u] = in ? __ldg(a.rho + (row0 + rb + u) * a.ld_rho + kk) : 0.0;
-            gv[u] = (in && has_g) ? __ldg(a.gamma + (row0 + rb + u) * a.ld_rho + kk) : 1.0;
-          }
-          double sa = 0.0, sl = 0.0;
+      if (KP <= 64 && DP4 <= 64) {
+        // common sizes: every global load of a 4-row step is issued before the first use (about 20 in flight per
+        // thread), so a step costs one memory latency instead of one per column block
+        for (int rb = pw * K2_PR; rb < TN; rb += 4 * K2_PR) {
+          double w[K2_PR], rv[K2_PR][2], gv[K2_PR][2], xv[K2_PR][2];
 #pragma unroll
           for (int u = 0; u < K2_PR; ++u) {
-            double v = rv[u] * w[u];
-            if (has_g) {
-              sa += v;
-              sl += (v != 0.0) ? v * log(gv[u]) : 0.0;        // feeds the dof condition, pmc.pyx:672-679
-              v *= gv[u];
+            const bool rin = rb + u < rows;
+            const int64_t row = row0 + rb + u;
+            w[u] = (a.sw && rin) ? __ldg(a.sw + row) : 1.0;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const int kk = lane + 32 * c;
+              const bool in = rin && kk < a.k;
+              rv[u][c] = in ? __ldg(a.rho + row * a.ld_rho + kk) : 0.0;
+              gv[u][c] = (in && has_g) ? __ldg(a.gamma + row * a.ld_rho + kk) : 1.0;
+              xv[u][c] = (rin && kk < D) ? __ldg(a.x + row * a.ldx + kk) : 0.0;
             }
-            if (rb + u < TN) Vs[(rb + u) * KP + kk] = v;
           }
-          if (has_g) { cs_a[kk] += sa; cs_a[KP + kk] += sl; }  // same thread every time: ordered, no race
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int kk = lane + 32 * c;                         // column of V and of Y handled by this lane
+            if (kk < KP) {
+              double sa = 0.0, sl = 0.0;
+#pragma unroll
+              for (int u = 0; u < K2_PR; ++u) {
+                double v = rv[u][c] * w[u];
+                if (has_g) {
+                  sa += v;
+                  sl += (v != 0.0) ? v * log(gv[u][c]) : 0.0;     // feeds the dof condition, pmc.pyx:672-679
+                  v *= gv[u][c];
+                }
+                if (rb + u < TN) Vs[(rb + u) * KP + kk] = v;
+              }
+              if (has_g) { cs_a[kk] += sa; cs_a[KP + kk] += sl; }  // same thread every time: ordered, no race
+            }
+            if (kk < DP4) {
+              const double sh = shift_s[kk];
+#pragma unroll
+              for (int u = 0; u < K2_PR; ++u) {
+                double y = 0.0;
+                if (rb + u < rows) y = (kk < D) ? (xv[u][c] - sh) : ((kk == D) ? 1.0 : 0.0);
+                if (rb + u < TN) Ys[(rb + u) * DP4 + kk] = y;
+              }
+            }
+          }
         }
-        for (int jj = lane; jj < DP4; jj += 32) {
-          double xv[K2_PR];
-#pragma unroll
-          for (int u = 0; u < K2_PR; ++u)
-            xv[u] = (rb + u < rows && jj < D) ? __ldg(a.x + (row0 + rb + u) * a.ldx + jj) : 0.0;
-          const double sh = shift_s[jj];
-#pragma unroll
-          for (int u = 0; u < K2_PR; ++u) {
-            double y = 0.0;
-            if (rb + u < rows) y = (jj < D) ? (xv[u] - sh) : ((jj == D) ? 1.0 : 0.0);
-            if (rb + u < TN) Ys[(rb + u) * DP4 + jj] = y;
+      } else {
+        for (int rb = pw * K2_PR; rb < TN; rb += 4 * K2_PR) {       // K2_PR rows in flight per warp
+          double w[K2_PR];
+  #pragma unroll
+          for (int u = 0; u < K2_PR; ++u) w[u] = (a.sw && rb + u < rows) ? __ldg(a.sw + row0 + rb + u) : 1.0;
+          for (int kk = lane; kk < KP; kk += 32) {
+            double rv[K2_PR], gv[K2_PR];
+  #pragma unroll
+            for (int u = 0; u < K2_PR; ++u) {
+              const bool in = (rb + u < rows) && (kk < a.k);
+              rv[u] = in ? __ldg(a.rho + (row0 + rb + u) * a.ld_rho + kk) : 0.0;
+              gv[u] = (in && has_g) ? __ldg(a.gamma + (row0 + rb + u) * a.ld_rho + kk) : 1.0;
+            }
+            double sa = 0.0, sl = 0.0;
+  #pragma unroll
+            for (int u = 0; u < K2_PR; ++u) {
+              double v = rv[u] * w[u];
+              if (has_g) {
+                sa += v;
+                sl += (v != 0.0) ? v * log(gv[u]) : 0.0;        // feeds the dof condition, pmc.pyx:672-679
+                v *= gv[u];
+              }
+              if (rb + u < TN) Vs[(rb + u) * KP + kk] = v;
+            }
+            if (has_g) { cs_a[kk] += sa; cs_a[KP + kk] += sl; }  // same thread every time: ordered, no race
+          }
+          for (int jj = lane; jj < DP4; jj += 32) {
+            double xv[K2_PR];
+  #pragma unroll
+            for (int u = 0; u < K2_PR; ++u)
+              xv[u] = (rb + u < rows && jj < D) ? __ldg(a.x + (row0 + rb + u) * a.ldx + jj) : 0.0;
+            const double sh = shift_s[jj];
+  #pragma unroll
+            for (int u = 0; u < K2_PR; ++u) {
+              double y = 0.0;
+              if (rb + u < rows) y = (jj < D) ? (xv[u] - sh) : ((jj == D) ? 1.0 : 0.0);
+              if (rb + u < TN) Ys[(rb + u) * DP4 + jj] = y;
+            }
           }
         }
       }
