@@ -93,8 +93,9 @@ def summarize_rep(rep, tag, traffic_for=None):
         wr = to_bytes(d["dram__bytes_write.sum"], u["dram__bytes_write.sum"])
         lines.append("| dram bytes per launch (read + write) | %.4g | byte |" % (rd + wr))
         st = None
+        base = kname.split("(")[0].split("<")[0].replace("void ", "").replace("pmc::", "")
         for name, val in stalls.items():
-            if name.split("(")[0].replace("void ", "") in kname:
+            if name.split("(")[0].split("<")[0].replace("void ", "").replace("pmc::", "") == base:
                 st = val
         if st and st["samples"]:
             lines += ["", "Warp-stall sampling (all samples = %d):" % st["samples"], "", "| reason | share |", "|---|---|"]
