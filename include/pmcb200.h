@@ -117,6 +117,20 @@ int pmcb200_mixture_eval_host(pmcb200_ctx* ctx,
                               const double* weights_host, double* sums_host,
                               int64_t chunk_rows);
 
+/* ---- K3: draw samples from the mixture on the device ------------------------------------------------
+ * Replaces MixtureDensity.propose density/mixture.pyx:159-212 with Gauss.propose density/gauss.pyx:159-163 /
+ * StudentT.propose density/student_t.pyx:49-55,172-176 underneath (one Python-level draw per sample there).
+ * starts_host [k+1]: first row of each component's block, from the caller's multinomial counts
+ * (mixture.pyx:193) -- rows [starts[c], starts[c+1]) are x = mean_c + L_c z [* sqrt(dof_c / chi2(dof_c))].
+ * Variates: Philox4x32-10, subsequence = index0 + row, so the result does not depend on the launch geometry;
+ * give each rank index0 = its global row offset.  latent_dev (int32 [n]) may be NULL.  chol is the lower
+ * Cholesky factor of every covariance ([k, d, d] row-major), dofs_dev NULL for a Gaussian mixture.
+ */
+int pmcb200_mixture_propose(pmcb200_ctx* ctx, int64_t n, int d, int k,
+                            const double* means_dev, const double* chol_dev, const double* dofs_dev,
+                            const int64_t* starts_host, uint64_t seed, uint64_t index0,
+                            double* x_dev, int64_t ldx, int* latent_dev, void* stream);
+
 /* ---- measurement helpers ---------------------------------------------------------------------------
  * FP64 FMA throughput of this device (register-resident DFMA chains on every SM), the roof that bounds
  * K1/K2.  which: 0 = DFMA only, 1 = DFMA + one broadcast LDS.128 per 4 DFMA,

@@ -1,6 +1,6 @@
 """Build the C-ABI shared library ``pypmc_b200/csrc/libpmcb200.so`` in-tree with nvcc for sm_100a.
 
-    python -m pypmc_b200._build [--force]
+    python pypmc_b200/_build.py [--force]      (run as a script: importing the package would load the stale library first)
 
 nvcc cross-compiles without a GPU.  The library travels to the GPU box with the repo snapshot; it is
 git-ignored.  Objects are rebuilt only when a source or header is newer.

@@ -42,6 +42,9 @@ SIGNATURES = {
     "pmcb200_mixture_eval_host": (ctypes.c_int, [
         _vp, _vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
         ctypes.c_double, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int64]),
+    "pmcb200_mixture_propose": (ctypes.c_int, [
+        _vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_uint64, ctypes.c_uint64, _vp,
+        ctypes.c_int64, _vp, _vp]),
     "pmcb200_fp64_peak": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _c_double_p, _c_double_p]),
     "pmcb200_launch_count": (ctypes.c_int64, [_vp]),
 }
@@ -151,6 +154,12 @@ class Context:
         _check(load().pmcb200_mixture_eval_host(self.handle, _ptr(x), n, ldx, d, _ptr(records), _ptr(cols), kl, k_out,
                                                 mode, max_init, _ptr(logq), _ptr(lp), _ptr(resp), _ptr(aux),
                                                 _ptr(weights), _ptr(sums), chunk_rows), "pmcb200_mixture_eval_host")
+
+    def mixture_propose(self, n, d, k, means, chol, dofs, starts, seed, index0, x, ldx, latent=None, stream=0):
+        starts = np.ascontiguousarray(starts, dtype=np.int64)
+        _check(load().pmcb200_mixture_propose(self.handle, n, d, k, _ptr(means), _ptr(chol), _ptr(dofs), starts.ctypes.data,
+                                              int(seed), int(index0), _ptr(x), ldx, _ptr(latent), stream),
+               "pmcb200_mixture_propose")
 
     def fp64_peak(self, which=0, iters=4000):
         g, ms = ctypes.c_double(), ctypes.c_double()

@@ -9,6 +9,7 @@
 #include "k1_dispatch.cuh"
 #include "k1_prepare.cuh"
 #include "k2_suffstats.cuh"
+#include "k3_propose.cuh"
 #include "microbench.cuh"
 
 namespace pmc {
@@ -85,6 +86,7 @@ struct pmcb200_ctx {
   int sm_count = 0;
   DevBuf ws;              // partial sums of K2 / microbenchmark scratch
   DevBuf k1ws;            // K1: derived records, shift, flag, per-warp partial sums (device-pointer entry point)
+  DevBuf pws;             // K3: block starts
   DevBuf k1row;           // K1: per-row (max, 1/denominator) handed from k1_fast_eval to k1_finish
   cudaStream_t copy_stream[2] = {nullptr, nullptr};
   // host pipeline: per-slot device buffers
@@ -138,7 +140,7 @@ int pmcb200_create(int device, pmcb200_ctx** out) {
 int pmcb200_destroy(pmcb200_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
-  DevBuf* all[] = {&c->ws, &c->k1ws, &c->k1row, &c->hrec, &c->hcols};
+  DevBuf* all[] = {&c->ws, &c->k1ws, &c->k1row, &c->pws, &c->hrec, &c->hcols};
   for (DevBuf* b : all)
     if (b->p) cudaFree(b->p);
   for (int i = 0; i < 2; ++i) {
@@ -407,6 +409,37 @@ int pmcb200_mixture_eval_host(pmcb200_ctx* c, const double* x, int64_t n, int64_
       sums[0] += chunk_sums[size_t(ci) * 2];
       sums[1] += chunk_sums[size_t(ci) * 2 + 1];
     }
+  return 0;
+}
+
+int pmcb200_mixture_propose(pmcb200_ctx* c, int64_t n, int d, int k, const double* means, const double* chol,
+                            const double* dofs, const int64_t* starts_host, uint64_t seed, uint64_t index0, double* x,
+                            int64_t ldx, int* latent, void* stream) {
+  PMC_REQUIRE(c != nullptr, "mixture_propose: NULL context");
+  PMC_REQUIRE(d >= 1 && d <= 256 && k >= 1 && n >= 0 && ldx >= d, "mixture_propose: bad sizes");
+  PMC_REQUIRE(starts_host != nullptr, "mixture_propose: NULL starts");
+  PMC_REQUIRE(starts_host[0] == 0 && starts_host[k] == n, "mixture_propose: starts must run from 0 to n");
+  for (int i = 0; i < k; ++i) PMC_REQUIRE(starts_host[i] <= starts_host[i + 1], "mixture_propose: starts must not decrease");
+  PMC_CUDA_CHECK(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n == 0) return 0;
+  PMC_REQUIRE(means && chol && x, "mixture_propose: NULL input");
+  if (int rc = ensure(c->pws, size_t(k + 1) * sizeof(int64_t))) return rc;
+  // pageable source: the copy is staged before the call returns, so the caller's array may die at once
+  PMC_CUDA_CHECK(cudaMemcpyAsync(c->pws.p, starts_host, size_t(k + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  ProposeArgs a{n, ldx, d, k, means, chol, dofs, static_cast<const int64_t*>(c->pws.p), seed, index0, x, latent};
+  const size_t smem = sizeof(double) * size_t(K3_THREADS) * (d | 1) + sizeof(int64_t) * size_t(k + 1) + 16;
+  PMC_REQUIRE(smem <= 200 * 1024, "mixture_propose: too many components for the shared-memory table");
+  static bool attr_set = false;
+  if (!attr_set) {
+    PMC_CUDA_CHECK(cudaFuncSetAttribute(k3_propose, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  const int64_t blocks = (n + K3_THREADS - 1) / K3_THREADS;
+  const int grid = int(std::min<int64_t>(blocks, int64_t(c->sm_count) * 8));
+  k3_propose<<<grid, K3_THREADS, smem, st>>>(a);
+  PMC_CUDA_CHECK(cudaGetLastError());
+  c->launches++;
   return 0;
 }
 

@@ -160,6 +160,45 @@ class MixtureDensity(ProbabilityDensity):
         return samples
 
 
+    def propose_device(self, N=1, rng=_np.random.mtrand, trace=False, shuffle=False, seed=None, index0=0, device=None):
+        """Draw ``N`` points on the GPU (kernel K3) and return them as a float64 CUDA tensor [N, dim] (with
+        ``trace`` also the int64 origin tensor, like :meth:`propose`).
+
+        The per-component counts come from ``rng.multinomial(N, self.weights)`` exactly as in the reference
+        (mixture.pyx:193) and the samples are laid out in component order; the normal / chi-square variates are a
+        Philox4x32-10 stream keyed by (``seed``, ``index0`` + row) -- ``seed`` defaults to a draw from ``rng``,
+        ``index0`` is this rank's global row offset when several ranks draw from one logical stream.
+        ``shuffle`` applies a device-side random permutation (off by default: importance sampling and the
+        PMC update do not depend on the order)."""
+        if trace and shuffle:
+            raise ValueError('Either ``shuffle`` or ``trace`` must be ``False``!')
+        mode = self._require_mode()
+        t = _dev.torch()
+        dev = "cuda:%d" % (_lib.default_device() if device is None else device)
+        counts = _np.asarray(rng.multinomial(N, self.weights), dtype=_np.int64)
+        starts = _np.concatenate([[0], _np.cumsum(counts)]).astype(_np.int64)
+        if seed is None:
+            seed = int(rng.randint(0, 2 ** 31 - 1))
+        k, d = len(self), self.dim
+        means = _dev.to_device(_np.array([c.mu for c in self.components], dtype=float).reshape(k, d), device)
+        chol_src = [c._local_gauss.cholesky_sigma if mode == _lib.MODE_GAUSS else c._local_t.cholesky_sigma
+                    for c in self.components]
+        chol = _dev.to_device(_np.array(chol_src, dtype=float).reshape(k, d, d), device)
+        dofs = None
+        if mode == _lib.MODE_STUDENT_T:
+            dofs = _dev.to_device(_np.array([c.dof for c in self.components], dtype=float), device)
+        x = t.empty((N, d), dtype=t.float64, device=dev)
+        latent = t.empty(N, dtype=t.int32, device=dev) if trace else None
+        _lib.Context.get(device).mixture_propose(N, d, k, means, chol, dofs, starts, seed, index0, x, d, latent,
+                                                 _dev.current_stream_ptr())
+        if trace:
+            return x, latent.to(t.int64)
+        if shuffle:
+            g = t.Generator(device=dev).manual_seed(seed)
+            x = x[t.randperm(N, device=dev, generator=g)]
+        return x
+
+
 def create_gaussian_mixture(means, covs, weights=None):
     """:class:`MixtureDensity` of :class:`Gauss` components (mixture.pyx:214-246)."""
     assert len(means) == len(covs), \

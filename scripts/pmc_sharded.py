@@ -1,11 +1,12 @@
-"""Config 5 (BASELINE.json): one PMC update (weight + E-pass + statistics + all-reduce + host update) with the
-samples sharded over the GPUs of one node.  Launch with torchrun; prints one JSON line on rank 0.
+"""Config 5 (BASELINE.json): one full PMC iteration -- propose on the device (K3), weight (2 x K1), update
+(K1 rho + K2 + all-reduce + host finishing) -- with the samples sharded over the GPUs of one node.  Launch with torchrun; prints one JSON line on rank 0.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
         scripts/pmc_sharded.py --rows 10000000 [--check]
 
 --check: rank 0 also runs the same update unsharded on the concatenated (small) data and compares at 1e-12.
-Samples are drawn on each rank's device from the proposal mixture (rank-offset seed); the target is a second
+Samples are drawn on each rank's device from the proposal mixture (kernel K3, one Philox stream indexed by the
+global row so that ranks never overlap); the target is a second
 K=32 Gaussian mixture evaluated with the same kernel K1, importance weight = exp(log p - log q) as in
 examples/pmc.py:30-32 of the reference.
 """
@@ -76,13 +77,22 @@ def main():
         target = create_gaussian_mixture(tm, pc, pw)
     else:
         target = create_gaussian_mixture(*synth_mixture(K, D, seed=3))
-    x = draw(n, pm, pc, pw, seed=100 + rank, device=dev)
+    rng = np.random.RandomState(100 + rank)
+    tsplit = {}
 
     def iteration():
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        x = prop.propose_device(n, rng, seed=777, index0=rank * n)   # K3 (multinomial counts on the host)
+        e[1].record()
         logq = prop.multi_evaluate(x)                       # K1 (proposal)
         logp = target.multi_evaluate(x)                     # K1 (target)
         wts = torch.exp(logp - logq)                        # importance weights
-        return gaussian_pmc(DeviceSamples(x, wts), prop)    # K1 (rho) + K2 + all-reduce + host update
+        e[2].record()
+        new = gaussian_pmc(DeviceSamples(x, wts), prop)     # K1 (rho) + K2 + all-reduce + host update
+        torch.cuda.synchronize()
+        tsplit.update(propose_ms=e[0].elapsed_time(e[1]), weight_ms=e[1].elapsed_time(e[2]), x=x)
+        return new
 
     new = iteration()                                        # warm-up
     torch.cuda.synchronize()
@@ -113,6 +123,7 @@ def main():
     check = None
     if args.check:
         # unsharded run of the same update on the gathered samples (small N only)
+        x = tsplit["x"]
         xs = [torch.empty_like(x) for _ in range(world)]
         if world > 1:
             dist.all_gather(xs, x)
@@ -129,8 +140,9 @@ def main():
                 errs.append(np.max(np.abs(c1.sigma - c2.sigma)) / np.max(np.abs(c1.sigma)))
             check = float(max(errs))
     if rank == 0:
-        print(json.dumps({"workload": "PMC iteration: 2x multi_evaluate + gaussian_pmc, N=%d/GPU K=%d D=%d" % (n, K, D),
+        print(json.dumps({"workload": "PMC iteration: propose + 2x multi_evaluate + gaussian_pmc, N=%d/GPU K=%d D=%d" % (n, K, D),
                           "n_gpus": world, "s_per_iteration": float(t[0]), "pairs_per_s": world * n * K / float(t[0]),
+                          "propose_ms": tsplit["propose_ms"], "weight_ms": tsplit["weight_ms"],
                           "ranks_identical": bool(ok.item()), "max_rel_diff_vs_unsharded": check,
                           "times": times}))
     if world > 1:

@@ -344,3 +344,46 @@ def test_full_size_properties(pm):
     run_k1(x, mix._packed(), K, _lib.MODE_GAUSS, resp=rho)
     ok = lq > -600
     assert float((rho.sum(1)[ok] - 1.0).abs().max()) < 1e-12
+
+
+# ------------------------------------------------------------------ K3: device-side propose (statistical parity)
+def test_propose_device_statistics(pm):
+    """K3 cannot be bit-identical to numpy's Mersenne Twister: check the block structure the
+    reference produces (mixture.pyx:193-212) exactly and the distribution statistically."""
+    import torch
+    from scipy import stats
+    from pypmc_b200.density.mixture import create_gaussian_mixture, create_t_mixture
+    K, D, N = 4, 5, 400_000
+    means, covs, w, _, _ = _synth(K, D, 10, seed=21)
+    mix = create_gaussian_mixture(means, covs, w)
+    rng = np.random.RandomState(5)
+    x, lat = mix.propose_device(N, rng, trace=True, seed=1234)
+    counts = np.random.RandomState(5).multinomial(N, mix.weights)          # same generator state as the call above
+    lat = lat.cpu().numpy()
+    np.testing.assert_array_equal(lat, np.repeat(np.arange(K), counts))   # component blocks in component order
+    xh = x.cpu().numpy()
+    chol = np.linalg.cholesky(covs)
+    for k in range(K):
+        xs = xh[lat == k]
+        z = np.linalg.solve(chol[k], (xs - means[k]).T).T                 # whitened: iid N(0, 1) if K3 is right
+        n = len(z)
+        assert np.abs(z.mean(0)).max() < 5.0 / np.sqrt(n)
+        assert np.abs(np.cov(z.T) - np.eye(D)).max() < 6.0 * np.sqrt(2.0 / n)
+        assert stats.kstest(z[:20000, 0], "norm").pvalue > 1e-4
+        assert stats.kstest(z[:20000, D - 1], "norm").pvalue > 1e-4
+    # reproducible, and independent of how the rows are split over launches / ranks
+    x2 = mix.propose_device(N, np.random.RandomState(5), seed=1234)
+    assert torch.equal(x, x2)
+    # Student-t: squared whitened radius / D is F(D, nu) distributed (student_t.pyx:49-55)
+    dofs = np.array([3.0, 4.5, 8.0, 0.7])
+    tm = create_t_mixture(means, covs, dofs, w)
+    xt, latt = tm.propose_device(N, np.random.RandomState(7), trace=True, seed=99)
+    xt, latt = xt.cpu().numpy(), latt.cpu().numpy()
+    for k in range(K):
+        xs = xt[latt == k][:50000]
+        z = np.linalg.solve(chol[k], (xs - means[k]).T).T
+        f = (z ** 2).sum(1) / D
+        assert stats.kstest(f, stats.f(D, dofs[k]).cdf).pvalue > 1e-4, k
+    # end to end: the importance weights of samples drawn from the mixture itself are all one
+    lq = mix.multi_evaluate(x)
+    assert bool(torch.isfinite(lq).all())
