@@ -4,7 +4,7 @@ Same class API as ``pypmc.density`` and ``pypmc.mix_adapt`` for that path; the N
 hand-written float64 CUDA kernels behind the C ABI of ``include/pmcb200.h``.  There is no CPU fallback.
 """
 from . import _lib
-from . import density, mix_adapt, tools  # noqa: F401
+from . import density, mix_adapt, sampler, tools  # noqa: F401
 
 __version__ = "0.1.0"
 

@@ -6,6 +6,8 @@ Run in the build container only (the reference does not travel to the GPU box):
     python -m pip install --no-index --no-build-isolation --no-deps \
         --find-links /opt/wheelhouse --target baseline/_ref /tmp/refbuild   # copy of /root/reference
     PYTHONPATH=baseline/_ref python tests/golden/make_golden.py
+    # or, against an in-place build of a scratch copy (cp -r /root/reference /tmp/refbuild; setup.py build_ext --inplace):
+    PYPMC_REF=/tmp/refbuild python tests/golden/make_golden.py [pmc_example]
 
 Every array written here is an output of the reference's own public API
 (``MixtureDensity.multi_evaluate``, ``gaussian_pmc``, ``student_t_pmc``,
@@ -21,7 +23,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+sys.path.insert(0, os.environ.get("PYPMC_REF", os.path.join(ROOT, "baseline", "_ref")))   # or an in-place build
 
 import pypmc  # noqa: E402  (the compiled reference)
 from pypmc.density.mixture import create_gaussian_mixture, create_t_mixture  # noqa: E402
@@ -29,7 +31,8 @@ from pypmc.mix_adapt.pmc import gaussian_pmc, student_t_pmc, PMC  # noqa: E402
 from pypmc.mix_adapt.variational import GaussianInference  # noqa: E402
 
 logging.getLogger("pypmc").setLevel(logging.ERROR)
-assert "baseline/_ref" in pypmc.__file__, pypmc.__file__
+assert "/root/repo/pypmc" not in pypmc.__file__ and ("baseline/_ref" in pypmc.__file__ or os.environ.get("PYPMC_REF")), \
+    pypmc.__file__
 
 
 def synth_mixture(K, D, seed=1, ridge=0.5, spread=3.0):
@@ -171,7 +174,51 @@ def vb_case(name, N, K, D, full=True, keep_rows=None):
     print(name)
 
 
+def pmc_example_case(name="pmc_example", seed=123456, steps=10, n_per_step=1000):
+    """BASELINE config 1: the loop of the reference's examples/pmc.py (bimodal 2-d Gaussian target, 3-component
+    initial proposal, ImportanceSampler.run + gaussian_pmc every 1000 samples) with a seeded global mtrand, plus
+    combine_weights over all steps (sampler/importance_sampling.py:238-371)."""
+    from copy import deepcopy
+    from pypmc.density.gauss import Gauss
+    from pypmc.density.mixture import MixtureDensity
+    from pypmc.sampler.importance_sampling import ImportanceSampler, combine_weights
+    t_means = [np.array([5.0, 0.01]), np.array([-4.0, 1.0])]
+    t_covs = [np.array([[0.01, 0.003], [0.003, 0.0025]]), np.array([[0.1, 0.0], [0.0, 0.02]])]
+    t_w = np.array([0.3, 0.7])
+    target = create_gaussian_mixture(t_means, t_covs, t_w)
+    p_means = [np.array([4.0, 0.0]), np.array([-5.0, 0.0]), np.array([0.0, 0.0])]
+    proposal = MixtureDensity([Gauss(m, np.eye(2)) for m in p_means])
+    np.random.seed(seed)
+    sampler = ImportanceSampler(target.evaluate, proposal)
+    out = dict(seed=np.array(seed), steps=np.array(steps), n_per_step=np.array(n_per_step), t_means=np.array(t_means),
+               t_covs=np.array(t_covs), t_w=t_w, p_means=np.array(p_means))
+    proposals = []
+    for i in range(steps):
+        proposals.append(deepcopy(sampler.proposal))
+        origin = sampler.run(n_per_step, trace_sort=True)
+        out["origin_%d" % i] = np.array(origin)
+        gaussian_pmc(sampler.samples[-1], sampler.proposal, sampler.weights[-1][:, 0], origin, mincount=20, rb=True,
+                     copy=False)
+        out.update(pack("prop_after_%d" % i, recover(sampler.proposal)))
+    out["samples"] = np.array(sampler.samples[:])
+    out["weights"] = np.array(sampler.weights[:][:, 0])
+    cw = combine_weights([sampler.samples[i] for i in range(steps)], [sampler.weights[i][:, 0] for i in range(steps)],
+                         proposals)
+    out["combined_weights"] = np.array(cw[:][:, 0])
+    # linear-scale branch: one non-positive weight
+    w_lin = [sampler.weights[i][:, 0].copy() for i in range(3)]
+    w_lin[1][5] = 0.0
+    cl = combine_weights([sampler.samples[i] for i in range(3)], w_lin, proposals[:3])
+    out["combined_weights_linear3"] = np.array(cl[:][:, 0])
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "pmc_example":
+        pmc_example_case()
+        sys.exit(0)
+    pmc_example_case()
     gauss_case("gauss_small", N=257, K=5, D=7, dead=(3,))
     gauss_case("gauss_c2", N=2048, K=32, D=30, full=False, keep_rows=128)  # BASELINE config 2 shape
     gauss_case("gauss_c2_stress", N=2048, K=32, D=30, ridge=1e-4, full=False, keep_rows=128)  # kappa ~ 3e4

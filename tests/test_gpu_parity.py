@@ -387,3 +387,50 @@ def test_propose_device_statistics(pm):
     # end to end: the importance weights of samples drawn from the mixture itself are all one
     lq = mix.multi_evaluate(x)
     assert bool(torch.isfinite(lq).all())
+
+
+# ------------------------------------------------------------------ config 1: the examples/pmc.py loop end to end
+def test_pmc_example_loop_matches_reference(pm, golden):
+    """BASELINE config 1: ImportanceSampler.run + gaussian_pmc every 1000 samples, 10 steps, seeded global mtrand,
+    replayed with this package's classes against the fixture the compiled reference produced
+    (tests/golden/make_golden.py::pmc_example_case).  The proposal draws go through numpy exactly as in the
+    reference, so the sample streams coincide and every later quantity can be compared number by number."""
+    from copy import deepcopy
+    from pypmc_b200.density.gauss import Gauss
+    from pypmc_b200.density.mixture import MixtureDensity, create_gaussian_mixture
+    from pypmc_b200.mix_adapt.pmc import gaussian_pmc
+    from pypmc_b200.sampler.importance_sampling import ImportanceSampler, combine_weights
+    g = golden("pmc_example")
+    steps, n = int(g["steps"]), int(g["n_per_step"])
+    target = create_gaussian_mixture(g["t_means"], g["t_covs"], g["t_w"])
+    proposal = MixtureDensity([Gauss(m, np.eye(2)) for m in g["p_means"]])
+    np.random.seed(int(g["seed"]))
+    sampler = ImportanceSampler(target.evaluate, proposal)
+    proposals = []
+    for i in range(steps):
+        proposals.append(deepcopy(sampler.proposal))
+        origin = sampler.run(n, trace_sort=True)
+        np.testing.assert_array_equal(origin, g["origin_%d" % i])
+        gaussian_pmc(sampler.samples[-1], sampler.proposal, sampler.weights[-1][:, 0], origin, mincount=20, rb=True,
+                     copy=False)
+        np.testing.assert_allclose(sampler.proposal.weights, g["prop_after_%d_weights" % i], rtol=1e-9, atol=1e-300)
+        live = sampler.proposal.weights != 0
+        mu = np.array([c.mu for c in sampler.proposal.components])
+        cov = np.array([c.sigma for c in sampler.proposal.components])
+        np.testing.assert_allclose(mu[live], g["prop_after_%d_means" % i][live], rtol=1e-9, atol=1e-12)
+        assert mat_err(cov[live], g["prop_after_%d_covs" % i][live]) < 1e-9
+    np.testing.assert_allclose(sampler.samples[:], g["samples"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(sampler.weights[:][:, 0], g["weights"], rtol=1e-9, atol=1e-300)
+    assert len(sampler.samples) == steps and sampler.samples[-1].shape == (n, 2)
+    # deterministic mixture weights over all steps, log-scale and linear-scale branches
+    cw = combine_weights([sampler.samples[i] for i in range(steps)], [sampler.weights[i][:, 0] for i in range(steps)],
+                         proposals)
+    np.testing.assert_allclose(cw[:][:, 0], g["combined_weights"], rtol=1e-9, atol=1e-300)
+    w_lin = [sampler.weights[i][:, 0].copy() for i in range(3)]
+    w_lin[1][5] = 0.0
+    cl = combine_weights([sampler.samples[i] for i in range(3)], w_lin, proposals[:3])
+    np.testing.assert_allclose(cl[:][:, 0], g["combined_weights_linear3"], rtol=1e-9, atol=1e-300)
+    # the batched weight pass equals the reference's per-sample formulation (SURVEY F2)
+    x5 = sampler.samples[0][:5]
+    per_sample = np.array([np.exp(target.evaluate(x) - proposals[0].evaluate(x)) for x in x5])
+    np.testing.assert_allclose(sampler.weights[0][:5, 0], per_sample, rtol=1e-10)

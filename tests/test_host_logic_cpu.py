@@ -145,3 +145,39 @@ def test_two_rank_gloo_sharded_update_matches_unsharded_oracle(tmp_path):
     np.testing.assert_allclose(res[0]["mean"], mu_ref, rtol=1e-11, atol=1e-13)
     assert mat_err(res[0]["cov"], cov_ref) < 1e-11
     assert float(res[0]["loglik"]) == pytest.approx(float((sw * logq).sum() / sw.sum()), rel=1e-13)
+
+
+def test_history_semantics():
+    # pypmc/tools/_history.py:7-116 (docstring example, views, negative indices, growth, clear)
+    from pypmc_b200.tools._history import History
+    h = History(2)
+    for i in range(2):
+        a = h.append(i + 1)
+        a[:] = i + 1
+    np.testing.assert_array_equal(h[0], [[1.0, 1.0]])
+    np.testing.assert_array_equal(h[1], [[2.0, 2.0], [2.0, 2.0]])
+    np.testing.assert_array_equal(h[:], [[1.0, 1.0], [2.0, 2.0], [2.0, 2.0]])
+    np.testing.assert_array_equal(h[-1], h[1])
+    assert len(h) == 2
+    h[0][0, 0] = 7.0                       # index access returns a reference
+    assert h[:][0, 0] == 7.0
+    big = h.append(1000)
+    big[:] = 3.0
+    assert h[:].shape == (1003, 2) and h[0:2].shape == (3, 2) and (h[2] == 3.0).all() and h[:][0, 0] == 7.0
+    with pytest.raises(NotImplementedError):
+        h[::2]
+    with pytest.raises(AssertionError):
+        h.append(0)
+    h.clear()
+    assert len(h) == 0 and h[:].size == 0
+
+
+def test_combine_weights_argument_checks():
+    from pypmc_b200.sampler.importance_sampling import combine_weights
+    x = [np.zeros((3, 2)), np.zeros((2, 2))]
+    with pytest.raises(AssertionError, match="importance-sampling runs but 1 weights"):
+        combine_weights(x, [np.ones(3)], [None, None])
+    with pytest.raises(AssertionError, match="proposal densities"):
+        combine_weights(x, [np.ones(3), np.ones(2)], [None])
+    with pytest.raises(AssertionError, match="Length of weights"):
+        combine_weights(x, [np.ones(3), np.ones(3)], [None, None])
