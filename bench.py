@@ -271,10 +271,10 @@ def run_gpu(args):
         return
 
     # ---- roofline: the binding roof is the FP64 FMA pipe, measured live; HBM fraction reported beside it.
-    # The timed region is short (steps x ~13 ms), so the burst DFMA figure is the denominator; a 2 s DFMA run
+    # The timed region is short (steps x ~13 ms), so the burst DFMA figure is the denominator; a 1 s DFMA run
     # (sustained, power/thermal steady state) is reported next to it.
     peak_gflops, _ = ctx.fp64_peak(0, 3000)
-    sustained_gflops, sustained_ms = ctx.fp64_peak(0, 250000)
+    sustained_gflops, sustained_ms = ctx.fp64_peak(0, 2500000)   # ~1 s per repetition
     kernel_ms = float(np.median(per_step))                # prepare + K1 (the exact-difference form returns at once)
     flops = FLOP_PER_PAIR * float(n) * K
     achieved_tf = flops / (kernel_ms * 1e-3) * 1e-12

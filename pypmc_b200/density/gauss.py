@@ -23,6 +23,12 @@ class LocalGauss(LocalDensity):
         self.dim = sigma.shape[0]
         self._compute_norm()
 
+    def __deepcopy__(self, memo):
+        new = self.__class__.__new__(self.__class__)
+        for key, val in self.__dict__.items():           # arrays are replaced, never written in place: copy them flat
+            new.__dict__[key] = val.copy() if isinstance(val, _np.ndarray) else val
+        return new
+
     def _compute_norm(self):
         # gauss.pyx:54-56
         self.log_normalization = -0.5 * self.dim * _np.log(2.0 * _np.pi) - 0.5 * self.log_det_sigma
@@ -55,6 +61,15 @@ class Gauss(ProbabilityDensity):
         self._record = None                # packed CUDA record, rebuilt lazily
         assert self.dim == self.sigma.shape[0], \
             "Dimensions of mean (%d) and covariance matrix (%d) do not match!" % (self.dim, self.sigma.shape[0])
+
+    def __deepcopy__(self, memo):
+        new = self.__class__.__new__(self.__class__)
+        new.__dict__.update(self.__dict__)
+        local = self._local_gauss.__deepcopy__(memo)
+        new._local_gauss = local
+        new.mu = self.mu.copy()
+        new.inv_sigma, new.log_det_sigma, new.sigma = local.inv_sigma, local.log_det_sigma, local.sigma
+        return new
 
     # -- CUDA record -----------------------------------------------------------------------------------
     _mode = _lib.MODE_GAUSS

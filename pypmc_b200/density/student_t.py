@@ -55,6 +55,15 @@ class StudentT(ProbabilityDensity):
         self._eval_prefactor = - .5 * (self.dof + self.dim)
         self._inv_dof = 1. / self.dof
 
+    def __deepcopy__(self, memo):
+        new = self.__class__.__new__(self.__class__)
+        new.__dict__.update(self.__dict__)
+        local = self._local_t.__deepcopy__(memo)
+        new._local_t = local
+        new.mu = self.mu.copy()
+        new.inv_sigma, new.log_det_sigma, new.sigma = local.inv_sigma, local.log_det_sigma, local.sigma
+        return new
+
     _mode = _lib.MODE_STUDENT_T
 
     def _packed_record(self):

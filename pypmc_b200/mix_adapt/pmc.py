@@ -69,6 +69,27 @@ def _mixture_shift(density, live):
     return (w[:, None] * mus).sum(axis=0) / w.sum()
 
 
+#: warn when the single-shift raw moments of K2 are expected to lose more than ~1e-10 relative accuracy
+_SHIFT_CONDITION_LIMIT = 1e5
+
+
+def _warn_if_ill_conditioned(density, live, shift):
+    """K2 accumulates second moments about ONE shift c; the covariance of component k then carries a relative
+    rounding error of about eps * (mu_k - c)^T Sigma_k^-1 (mu_k - c) (the reference centres each component on its
+    own mean, pmc.pyx:200-204).  Components that far from the bulk are flagged, not silently degraded."""
+    worst, which = 0.0, -1
+    for k in live:
+        comp = density.components[k]
+        dlt = comp.mu - shift
+        q = float(dlt @ comp.inv_sigma @ dlt)
+        if q > worst:
+            worst, which = q, k
+    if worst > _SHIFT_CONDITION_LIMIT:
+        logger.warning("Component %i lies %.3g standard deviations from the common shift of the moment kernel; its "
+                       "updated covariance is accurate to about %.1e relative only." % (which, worst ** 0.5, 2.2e-16 * worst))
+    return worst
+
+
 def _e_pass_and_stats(ds, density, live, rb, mode):
     """K1 + K2 on this rank's samples, all-reduce, return (layout, unpacked statistics, shift)."""
     t = _dev.torch()
@@ -110,6 +131,7 @@ def _e_pass_and_stats(ds, density, live, rb, mode):
         packet[lay.off_counts:lay.off_counts + K] = t.bincount(lat[inside], minlength=K)[:K].to(t.float64)
 
     shift = _mixture_shift(density, live) if live else _np.zeros(D)
+    _warn_if_ill_conditioned(density, live, shift)
     _lib.Context.get().suffstats(ds.x, N, ds.x.stride(0) if N > 1 else D, D, _dev.to_device(shift), ds.rho, gamma, K, K,
                                  ds.w, packet, _dev.current_stream_ptr())
     _parallel.allreduce_(packet)

@@ -6,10 +6,20 @@ pmc.pyx:234-244).  ``tri_from_chol`` / ``tri_from_precision`` produce the lower-
 T^T T = M^-1 resp. = W that kernel K1 multiplies with (x - mu); they replace the explicit-inverse
 bilinear form ``bilinear_sym`` (_linalg.pyx:10-39) of the reference's inner loop.
 """
+import functools as _functools
+
 import numpy as _np
 from scipy.linalg import cholesky as _cholesky
-from scipy.linalg import solve_triangular as _solve_triangular
 from scipy.linalg.lapack import get_lapack_funcs as _get_lapack_funcs
+
+# float64 LAPACK routines, looked up once (scipy's wrappers re-validate their input on every call, which costs
+# more than the factorisation of a 30 x 30 matrix; the update calls this K times per iteration)
+_potri, _trtri = _get_lapack_funcs(("potri", "trtri"), (_np.empty((1, 1)),))
+
+
+@_functools.lru_cache(maxsize=64)
+def _strict_lower(d):
+    return _np.tril_indices(d, -1)
 
 
 def chol_inv_det(m):
@@ -18,17 +28,24 @@ def chol_inv_det(m):
     Raises ``numpy.linalg.LinAlgError`` if ``m`` is not symmetric, not positive definite or has a
     non-finite log-determinant; ``ValueError`` for non-finite input (``asarray_chkfinite``).
     """
-    m = _np.asarray_chkfinite(m)
-    if not _np.allclose(m, m.T):
+    m = _np.asarray_chkfinite(m, dtype=float)
+    if m.ndim != 2 or m.shape[0] != m.shape[1]:
+        raise ValueError("expected square matrix")
+    # numpy.allclose(m, m.T) for finite input (_linalg.pyx:62): |m - m^T| <= atol + rtol |m^T|
+    if not (_np.abs(m - m.T) <= 1e-8 + 1e-5 * _np.abs(m.T)).all():
         raise _np.linalg.LinAlgError("matrix not symmetric:\n" + repr(m))
-    low = _cholesky(m, lower=True)                       # LinAlgError when not positive definite
-    potri, = _get_lapack_funcs(("potri",), (m,))
-    inv, info = potri(low, lower=True)
+    # the reference's own call (_linalg.pyx:67); LinAlgError when not positive definite.  (Calling LAPACK potrf
+    # directly is faster but takes the other triangle's code path for C-ordered input: last-bit differences.)
+    low = _cholesky(m, lower=True, check_finite=False)
+    inv, info = _potri(low, lower=True)
     if info != 0:
         raise _np.linalg.LinAlgError("potri failed with info=%d" % info)
-    rows, cols = _np.tril_indices(len(m), -1)
+    rows, cols = _strict_lower(len(m))
     inv[cols, rows] = inv[rows, cols]                    # potri fills one triangle only
-    log_det = 2.0 * float(_np.sum(_np.log(_np.diag(low))))
+    log_det = 0.0
+    for v in _np.log(low.diagonal()).tolist():           # summed in index order like _linalg.pyx:84-90
+        log_det += v
+    log_det *= 2.0
     if not _np.isfinite(log_det):
         raise _np.linalg.LinAlgError("Nonpositive eigenvalues lead to invalid determinant " + repr(log_det))
     return low, inv, log_det
@@ -36,7 +53,10 @@ def chol_inv_det(m):
 
 def tri_from_chol(low):
     """T = L^-1 (lower triangular), so that ||T y||^2 = y^T (L L^T)^-1 y."""
-    return _solve_triangular(low, _np.eye(len(low)), lower=True)
+    t, info = _trtri(low, lower=1)
+    if info != 0:
+        raise _np.linalg.LinAlgError("trtri failed with info=%d" % info)
+    return _np.tril(t)
 
 
 def tri_from_precision(w):

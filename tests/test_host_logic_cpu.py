@@ -181,3 +181,16 @@ def test_combine_weights_argument_checks():
         combine_weights(x, [np.ones(3), np.ones(2)], [None])
     with pytest.raises(AssertionError, match="Length of weights"):
         combine_weights(x, [np.ones(3), np.ones(3)], [None, None])
+
+
+def test_shift_conditioning_warning(caplog):
+    import logging
+    from pypmc_b200.mix_adapt.pmc import _warn_if_ill_conditioned
+    from pypmc_b200.density.mixture import create_gaussian_mixture
+    ok = create_gaussian_mixture([[0.0, 0.0], [3.0, 1.0]], [np.eye(2), np.eye(2)])
+    far = create_gaussian_mixture([[0.0, 0.0], [3.0e4, 1.0]], [np.eye(2) * 1e-2, np.eye(2) * 1e-2])
+    with caplog.at_level(logging.WARNING, logger="pypmc_b200.mix_adapt.pmc"):
+        assert _warn_if_ill_conditioned(ok, [0, 1], np.array([1.5, 0.5])) < 10
+        assert not caplog.records
+        assert _warn_if_ill_conditioned(far, [0, 1], np.array([1.5e4, 0.5])) > 1e9
+        assert "standard deviations from the common shift" in caplog.text
