@@ -173,12 +173,21 @@ __global__ void __launch_bounds__(FastCfg<DP>::NW * 32, 1) k1_fast_eval(const Fa
         for (int p = 0; p <= r; ++p) {
           const double2 t0 = *reinterpret_cast<const double2*>(rec + 2 * r * (r + 1) + 4 * p);
           const double2 t1 = *reinterpret_cast<const double2*>(rec + 2 * r * (r + 1) + 4 * p + 2);
+          // snake order over the 2 x S outer product of each column: consecutive DFMAs share T or x alternately, so
+          // each needs one new register operand plus its accumulator (the register file delivers ~1 64-bit warp
+          // operand per clock per sub-partition, a DFMA wants three: scripts/ubench/dfma_rf.cu, dfma_snake.cu)
 #pragma unroll
-          for (int s = 0; s < S; ++s) {
-            z0[s] = fma(t0.x, xr[s][2 * p], z0[s]);
-            if (p < r) z0[s] = fma(t0.y, xr[s][2 * p + 1], z0[s]);     // T[2r][2r+1] == 0
-            z1[s] = fma(t1.x, xr[s][2 * p], z1[s]);
-            z1[s] = fma(t1.y, xr[s][2 * p + 1], z1[s]);
+          for (int s = 0; s < S; ++s) z0[s] = fma(t0.x, xr[s][2 * p], z0[s]);
+#pragma unroll
+          for (int s = S - 1; s >= 0; --s) z1[s] = fma(t1.x, xr[s][2 * p], z1[s]);
+          if (p < r) {                                                 // T[2r][2r+1] == 0
+#pragma unroll
+            for (int s = 0; s < S; ++s) z0[s] = fma(t0.y, xr[s][2 * p + 1], z0[s]);
+#pragma unroll
+            for (int s = S - 1; s >= 0; --s) z1[s] = fma(t1.y, xr[s][2 * p + 1], z1[s]);
+          } else {
+#pragma unroll
+            for (int s = 0; s < S; ++s) z1[s] = fma(t1.y, xr[s][2 * p + 1], z1[s]);
           }
         }
 #pragma unroll

@@ -273,10 +273,12 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_suffstats(const StatsArgs a)
         acc[2 * c][1] = fma(v.x, f1, acc[2 * c][1]);
         acc[2 * c][2] = fma(v.x, f2, acc[2 * c][2]);
         acc[2 * c][3] = fma(v.x, f3, acc[2 * c][3]);
-        acc[2 * c + 1][0] = fma(v.y, f0, acc[2 * c + 1][0]);
-        acc[2 * c + 1][1] = fma(v.y, f1, acc[2 * c + 1][1]);
-        acc[2 * c + 1][2] = fma(v.y, f2, acc[2 * c + 1][2]);
+        // snake order: consecutive DFMAs share v or f alternately, so each needs one new register operand plus its
+        // accumulator -- the register file delivers ~1 64-bit warp operand per clock (scripts/ubench/dfma_snake.cu)
         acc[2 * c + 1][3] = fma(v.y, f3, acc[2 * c + 1][3]);
+        acc[2 * c + 1][2] = fma(v.y, f2, acc[2 * c + 1][2]);
+        acc[2 * c + 1][1] = fma(v.y, f1, acc[2 * c + 1][1]);
+        acc[2 * c + 1][0] = fma(v.y, f0, acc[2 * c + 1][0]);
       }
     }
     mbar_arrive(&empty[s]);                                     // the producer may refill this stage
