@@ -40,6 +40,87 @@ class PacketLayout:
                     sumw=float(packet[self.off_sumw]), sum_a=float(packet[self.off_sum_a]))
 
 
+#: largest squared Mahalanobis distance (mu_k - c)^T Sigma_k^-1 (mu_k - c) tolerated between a component and the
+#: shift c its raw moments are taken about: the covariance then carries ~eps * 1e4 = 2e-12 relative rounding error
+SHIFT_CONDITION_LIMIT = 1.0e4
+
+
+def shift_groups(centers, precisions, weights, live, limit=SHIFT_CONDITION_LIMIT):
+    """Partition the live components into groups that share one shift vector for kernel K2.
+
+    K2 accumulates raw second moments about a shift c; the covariance of component k recovered from them loses
+    about eps * q_k(c), q_k(c) = (mu_k - c)^T P_k (mu_k - c), to cancellation (the reference centres every component
+    on its own new mean, pmc.pyx:200-204 / variational.pyx:876-890, and has no such term).  Normally ONE group --
+    shift = weighted centre of the mixture -- keeps every q_k below ``limit`` and K2 runs once.  Components that
+    are far apart in units of their own width are put into separate groups, greedily in component order, and K2
+    runs once per group on that group's columns: slower, never less accurate.
+
+    Returns a list of ``(indices, shift)``; deterministic, so every rank forms the same groups.
+    """
+    live = list(live)
+    if not live:
+        return []
+
+    def centre(idx):
+        w = np.array([weights[k] for k in idx], dtype=float)
+        mus = np.array([centers[k] for k in idx], dtype=float)
+        if not np.isfinite(w).all() or w.sum() <= 0:
+            return mus.mean(axis=0)
+        return (w[:, None] * mus).sum(axis=0) / w.sum()
+
+    def worst(idx, c):
+        q = 0.0
+        for k in idx:
+            d = centers[k] - c
+            q = max(q, float(d @ precisions[k] @ d))
+        return q
+
+    c_all = centre(live)
+    if not (worst(live, c_all) > limit):          # also taken when the estimate is NaN: one group, like before
+        return [(live, c_all)]
+    groups = []
+    for k in live:
+        for g in groups:
+            cand = g[0] + [k]
+            c = centre(cand)
+            if worst(cand, c) <= limit:
+                g[0], g[1] = cand, c
+                break
+        else:
+            groups.append([[k], np.array(centers[k], dtype=float)])
+    return [(g[0], g[1]) for g in groups]
+
+
+def grouped_suffstats(ctx, ds, lay, packet, groups, rho, gamma, stream):
+    """Run K2 once per shift group and leave the K statistics rows in ``packet`` (device).  Returns the per-component
+    shift array [K, D] the rows refer to (zeros for components in no group)."""
+    from .. import _device as dev
+    K, D, N = lay.K, lay.D, ds.N
+    shifts = np.zeros((K, D))
+    ldx = ds.x.stride(0) if N > 1 else D
+    if len(groups) == 1 and len(groups[0][0]) > 0 and _is_full(groups[0][0], K):
+        idx, c = groups[0]
+        shifts[:] = c
+        ctx.suffstats(ds.x, N, ldx, D, dev.to_device(c), rho, gamma, K, K, ds.w, packet, stream)
+        return shifts
+    t = dev.torch()
+    rows = packet[:lay.stats_len].view(K, lay.row)
+    rows.zero_()
+    for idx, c in groups:
+        cols = t.tensor(idx, device=rho.device)
+        rho_g = rho.index_select(1, cols).contiguous()
+        gamma_g = None if gamma is None else gamma.index_select(1, cols).contiguous()
+        out = t.empty((len(idx), lay.row), dtype=t.float64, device=rho.device)
+        ctx.suffstats(ds.x, N, ldx, D, dev.to_device(c), rho_g, gamma_g, len(idx), len(idx), ds.w, out, stream)
+        rows[cols] = out
+        shifts[idx] = c
+    return shifts
+
+
+def _is_full(idx, K):
+    return len(idx) == K and list(idx) == list(range(K))
+
+
 def moments_from_stats(st, shift, mean_norm: str):
     """Turn the shifted raw moments into the reference's two-pass quantities.
 
@@ -53,7 +134,8 @@ def moments_from_stats(st, shift, mean_norm: str):
     B = regularize(st["B"].copy())
     m, R = st["m"], st["R"]
     delta = m / B[:, None]                                   # mean - shift
-    mean = shift[None, :] + delta
+    shift = np.asarray(shift, dtype=float)
+    mean = (shift[None, :] if shift.ndim == 1 else shift) + delta   # one shift, or one per component (shift_groups)
     # sum v (y - delta)(y - delta)^T = R - delta m^T - m delta^T + B_true delta delta^T
     outer_dm = delta[:, :, None] * m[:, None, :]
     cov = R - outer_dm - np.swapaxes(outer_dm, 1, 2) + st["B"][:, None, None] * (delta[:, :, None] * delta[:, None, :])

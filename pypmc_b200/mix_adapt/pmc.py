@@ -23,7 +23,7 @@ from ..density._eval import run_k1
 from .. import _device as _dev
 from .. import _lib
 from .. import parallel as _parallel
-from ._stats import PacketLayout, moments_from_stats
+from ._stats import PacketLayout, moments_from_stats, shift_groups, grouped_suffstats
 
 logger = logging.getLogger(__name__)
 
@@ -58,36 +58,6 @@ def _check_arguments(samples, weights, latent, mincount, rb):
             raise ValueError('`mincount` must be 0 if `latent` is not provided!')
         if not rb:
             raise ValueError('`rb` must be True if `latent` is not provided!')
-
-
-def _mixture_shift(density, live):
-    """Shift vector for K2's raw moments: the weight-averaged centre of the live components."""
-    w = _np.array([density.weights[k] for k in live], dtype=float)
-    mus = _np.array([density.components[k].mu for k in live], dtype=float)
-    if not _np.isfinite(w).all() or w.sum() <= 0:
-        return mus.mean(axis=0)
-    return (w[:, None] * mus).sum(axis=0) / w.sum()
-
-
-#: warn when the single-shift raw moments of K2 are expected to lose more than ~1e-10 relative accuracy
-_SHIFT_CONDITION_LIMIT = 1e5
-
-
-def _warn_if_ill_conditioned(density, live, shift):
-    """K2 accumulates second moments about ONE shift c; the covariance of component k then carries a relative
-    rounding error of about eps * (mu_k - c)^T Sigma_k^-1 (mu_k - c) (the reference centres each component on its
-    own mean, pmc.pyx:200-204).  Components that far from the bulk are flagged, not silently degraded."""
-    worst, which = 0.0, -1
-    for k in live:
-        comp = density.components[k]
-        dlt = comp.mu - shift
-        q = float(dlt @ comp.inv_sigma @ dlt)
-        if q > worst:
-            worst, which = q, k
-    if worst > _SHIFT_CONDITION_LIMIT:
-        logger.warning("Component %i lies %.3g standard deviations from the common shift of the moment kernel; its "
-                       "updated covariance is accurate to about %.1e relative only." % (which, worst ** 0.5, 2.2e-16 * worst))
-    return worst
 
 
 def _e_pass_and_stats(ds, density, live, rb, mode):
@@ -130,10 +100,16 @@ def _e_pass_and_stats(ds, density, live, rb, mode):
         inside = (lat >= 0) & (lat < K)
         packet[lay.off_counts:lay.off_counts + K] = t.bincount(lat[inside], minlength=K)[:K].to(t.float64)
 
-    shift = _mixture_shift(density, live) if live else _np.zeros(D)
-    _warn_if_ill_conditioned(density, live, shift)
-    _lib.Context.get().suffstats(ds.x, N, ds.x.stride(0) if N > 1 else D, D, _dev.to_device(shift), ds.rho, gamma, K, K,
-                                 ds.w, packet, _dev.current_stream_ptr())
+    # shift vector(s) of the raw moments: one for the whole mixture unless components lie > 100 sigma apart
+    groups = shift_groups([c.mu for c in density.components], [c.inv_sigma for c in density.components],
+                          density.weights, live) if live else []
+    if len(groups) > 1:
+        logger.info("moment kernel: %d shift groups (components far apart in units of their width)" % len(groups))
+    if len(groups) <= 1:
+        # ONE launch over all K columns (dead components hold rho = 0 and come out as zero rows)
+        centre = groups[0][1] if groups else _np.zeros(D)
+        groups = [(list(range(K)), centre)]
+    shift = grouped_suffstats(_lib.Context.get(), ds, lay, packet, groups, ds.rho, gamma, _dev.current_stream_ptr())
     _parallel.allreduce_(packet)
     return lay, lay.unpack(packet.cpu().numpy()), shift
 

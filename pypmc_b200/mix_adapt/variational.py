@@ -23,7 +23,7 @@ from ..tools._linalg import chol_inv_det, tri_from_precision
 from .. import _device as _dev
 from .. import _lib
 from .. import parallel as _parallel
-from ._stats import PacketLayout, moments_from_stats
+from ._stats import PacketLayout, moments_from_stats, shift_groups, grouped_suffstats
 from .pmc import DeviceSamples
 
 logger = logging.getLogger(__name__)
@@ -241,9 +241,10 @@ class GaussianInference(object):
         packet = t.zeros(lay.size, dtype=t.float64, device=ds.x.device)
         run_k1(ds.x, packed, K, _lib.MODE_VB, lp=self._log_rho_dev, resp=self._r_dev, weights=ds.w,
                sums=packet[lay.off_sum_a:lay.off_sum_a + 2])
-        shift = (self.alpha[:, None] * self.m).sum(axis=0) / self.alpha.sum()
-        _lib.Context.get().suffstats(ds.x, n, ds.x.stride(0) if n > 1 else D, D, _dev.to_device(shift), self._r_dev, None,
-                                     K, K, ds.w, packet, _dev.current_stream_ptr())
+        # shift vector(s) of the raw moments: one (alpha-weighted centre) unless components lie > 100 sigma apart;
+        # component k is N(m_k, (nu_k W_k)^-1) in expectation
+        groups = shift_groups(self.m, self.nu[:, None, None] * self.W, self.alpha, range(K))
+        shift = grouped_suffstats(_lib.Context.get(), ds, lay, packet, groups, self._r_dev, None, _dev.current_stream_ptr())
         _parallel.allreduce_(packet)
         st = lay.unpack(packet.cpu().numpy())
         self._estep_packed = packed

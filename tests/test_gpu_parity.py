@@ -434,3 +434,49 @@ def test_pmc_example_loop_matches_reference(pm, golden):
     x5 = sampler.samples[0][:5]
     per_sample = np.array([np.exp(target.evaluate(x) - proposals[0].evaluate(x)) for x in x5])
     np.testing.assert_allclose(sampler.weights[0][:5, 0], per_sample, rtol=1e-10)
+
+
+# ------------------------------------------------------------------ K1 fallback: exact-difference form
+def test_exact_difference_fallback_far_narrow_components(pm, orc):
+    """Components that lie > 1e4 standard deviations from the common shift make k1_prepare raise its flag: the
+    exact-difference kernel (y = x - mu_k per component, k1_mixture_eval.cuh) must then produce the launch's
+    outputs -- log q, individual, rho, gamma and the fused sums -- to the same tolerance."""
+    import torch
+    from pypmc_b200.density.mixture import create_gaussian_mixture, create_t_mixture
+    from pypmc_b200.density._eval import run_k1
+    from pypmc_b200.mix_adapt.pmc import gaussian_pmc
+    from pypmc_b200 import _lib
+    rng = np.random.default_rng(17)
+    K, D, N = 3, 6, 3000
+    means = np.array([[-2.0e3] * D, [0.5] * D, [3.0e3] * D]) + rng.normal(size=(K, D))
+    covs = np.array([(lambda a: (a @ a.T + np.eye(D)) * 1e-4)(rng.normal(0, 0.3, size=(D, D))) for _ in range(K)])
+    w = np.array([0.3, 0.5, 0.2])
+    comp = rng.integers(0, K, size=N)
+    x = means[comp] + np.einsum("nij,nj->ni", np.linalg.cholesky(covs)[comp], rng.normal(size=(N, D)))
+    # |b| = |T (mu - c)| ~ 2e3 / 1e-2 = 2e5 > 1e4: the flag is up
+    for dofs in (None, np.array([3.0, 5.0, 7.0])):
+        comps = orc.Components(means, covs, dofs)
+        lq_ref, ind_ref = orc.mixture_multi_evaluate(x, comps, w)
+        mix = create_gaussian_mixture(means, covs, w) if dofs is None else create_t_mixture(means, covs, dofs, w)
+        ind = np.empty((N, K))
+        lq = mix.multi_evaluate(x, individual=ind)
+        assert rel_err(lq, lq_ref) < TOL
+        assert rel_err(ind, ind_ref) < TOL
+        rho_ref, _ = orc.calculate_rho_rb(x, comps, w)
+        xd = torch.from_numpy(x).cuda()
+        rho = torch.empty((N, K), dtype=torch.float64, device="cuda")
+        aux = torch.empty((N, K), dtype=torch.float64, device="cuda")
+        mode = _lib.MODE_GAUSS if dofs is None else _lib.MODE_STUDENT_T
+        sums = run_k1(xd, mix._packed(), K, mode, resp=rho, aux=aux, want_sums=True).cpu().numpy()
+        assert rel_err(rho.cpu().numpy(), rho_ref, floor=1e-280) < 1e-9
+        assert sums[0] == pytest.approx(float(lq_ref.sum()), rel=1e-12) and sums[1] == N
+        if dofs is not None:
+            assert rel_err(aux.cpu().numpy(), orc.student_t_gamma(x, comps)) < TOL
+    # and the update on top of it: the moment kernel runs once per shift group here (mix_adapt/_stats.py)
+    mix = create_gaussian_mixture(means, covs, w)
+    new = gaussian_pmc(x, mix)
+    rho_ref, _ = orc.calculate_rho_rb(x, orc.Components(means, covs), w)
+    alpha, mu, cov = orc.pmc_moments(x, rho_ref)
+    np.testing.assert_allclose(new.weights, alpha, rtol=1e-10)
+    np.testing.assert_allclose([c.mu for c in new.components], mu, rtol=1e-10)
+    assert mat_err(np.array([c.sigma for c in new.components]), cov) < TOL     # three shift groups: no cancellation

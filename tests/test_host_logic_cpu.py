@@ -183,14 +183,20 @@ def test_combine_weights_argument_checks():
         combine_weights(x, [np.ones(3), np.ones(3)], [None, None])
 
 
-def test_shift_conditioning_warning(caplog):
-    import logging
-    from pypmc_b200.mix_adapt.pmc import _warn_if_ill_conditioned
-    from pypmc_b200.density.mixture import create_gaussian_mixture
-    ok = create_gaussian_mixture([[0.0, 0.0], [3.0, 1.0]], [np.eye(2), np.eye(2)])
-    far = create_gaussian_mixture([[0.0, 0.0], [3.0e4, 1.0]], [np.eye(2) * 1e-2, np.eye(2) * 1e-2])
-    with caplog.at_level(logging.WARNING, logger="pypmc_b200.mix_adapt.pmc"):
-        assert _warn_if_ill_conditioned(ok, [0, 1], np.array([1.5, 0.5])) < 10
-        assert not caplog.records
-        assert _warn_if_ill_conditioned(far, [0, 1], np.array([1.5e4, 0.5])) > 1e9
-        assert "standard deviations from the common shift" in caplog.text
+def test_shift_groups():
+    """One shift for the whole mixture unless components are far apart in units of their own width (then K2 runs
+    once per group); deterministic and covering every live component exactly once."""
+    from pypmc_b200.mix_adapt._stats import shift_groups, SHIFT_CONDITION_LIMIT
+    eye = np.eye(2)
+    near = shift_groups([np.zeros(2), np.array([3.0, 1.0])], [eye, eye], [0.5, 0.5], [0, 1])
+    assert len(near) == 1 and near[0][0] == [0, 1]
+    np.testing.assert_allclose(near[0][1], [1.5, 0.5])
+    mus = [np.zeros(2), np.array([3.0e4, 1.0]), np.array([1.0, 0.0]), np.array([3.0e4, 2.0]), np.array([-5e5, 0.0])]
+    prec = [eye * 1e2] * 5
+    far = shift_groups(mus, prec, [0.2] * 5, [0, 1, 2, 3, 4])
+    assert sorted(sum((g[0] for g in far), [])) == [0, 1, 2, 3, 4]
+    assert [g[0] for g in far] == [[0, 2], [1, 3], [4]]
+    for idx, c in far:
+        assert max(float((mus[k] - c) @ prec[k] @ (mus[k] - c)) for k in idx) <= SHIFT_CONDITION_LIMIT
+    assert shift_groups(mus, prec, [0.2] * 5, [1, 3]) == [] or len(shift_groups(mus, prec, [0.2] * 5, [1, 3])) == 1
+    assert shift_groups(mus, prec, [0.2] * 5, []) == []
