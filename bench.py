@@ -306,9 +306,12 @@ def run_gpu(args):
     probe_value, _ = cpu_arm(probe_rows, 1, 1, threads, x=xh)
     cpu_rows = int(min(e2e_rows, max(probe_rows, 15.0 * probe_value / K)))
     cpu_value, cpu_dt = cpu_arm(cpu_rows, 1, 0, threads, x=xh)
+    one_rows = int(min(e2e_rows, 100_000))                 # the reference as shipped is single-threaded
+    one_value, one_dt = cpu_arm(one_rows, 1, 0, 1, x=xh)
     cpu = {"value": cpu_value, "unit": "pairs/s", "cores": threads, "kind": "port",
            "sample": "first %d of %d rows of the same workload, 1 timed pass (%.1f s), oracle/pmc_oracle.c over %d threads"
-                     % (cpu_rows, n, cpu_dt, threads)}
+                     % (cpu_rows, n, cpu_dt, threads),
+           "value_1_core": one_value, "sample_1_core": "first %d rows, 1 thread (%.1f s)" % (one_rows, one_dt)}
 
     print(json.dumps({
         "metric": "sample-component evals/sec (N*K/s)", "value": value, "unit": "pairs/s", "n_gpus": world,
