@@ -480,3 +480,20 @@ def test_exact_difference_fallback_far_narrow_components(pm, orc):
     np.testing.assert_allclose(new.weights, alpha, rtol=1e-10)
     np.testing.assert_allclose([c.mu for c in new.components], mu, rtol=1e-10)
     assert mat_err(np.array([c.sigma for c in new.components]), cov) < TOL     # three shift groups: no cancellation
+
+
+def test_empty_and_single_row_inputs(pm):
+    """Edge sizes: N = 0 returns empty outputs without a launch, N = 1 works, device weight diagnostics agree with numpy."""
+    import torch
+    from pypmc_b200.density.mixture import create_gaussian_mixture
+    from pypmc_b200.tools.convergence import perp, ess
+    means, covs, w, x, sw = _synth(3, 4, 50, seed=2)
+    mix = create_gaussian_mixture(means, covs, w)
+    assert mix.multi_evaluate(np.empty((0, 4))).shape == (0,)
+    ind = np.empty((0, 3))
+    assert mix.multi_evaluate(np.empty((0, 4)), individual=ind).shape == (0,)
+    assert mix.multi_evaluate(torch.empty((0, 4), dtype=torch.float64, device="cuda")).shape == (0,)
+    one = mix.multi_evaluate(x[:1])
+    assert one.shape == (1,) and one[0] == pytest.approx(mix.multi_evaluate(x)[0], rel=1e-14)
+    wd = torch.from_numpy(sw).cuda()
+    assert perp(wd) == pytest.approx(perp(sw), rel=1e-12) and ess(wd) == pytest.approx(ess(sw), rel=1e-12)

@@ -200,3 +200,15 @@ def test_shift_groups():
         assert max(float((mus[k] - c) @ prec[k] @ (mus[k] - c)) for k in idx) <= SHIFT_CONDITION_LIMIT
     assert shift_groups(mus, prec, [0.2] * 5, [1, 3]) == [] or len(shift_groups(mus, prec, [0.2] * 5, [1, 3])) == 1
     assert shift_groups(mus, prec, [0.2] * 5, []) == []
+
+
+def test_perp_and_ess_reference_values():
+    # pypmc/tools/convergence.py:6-72: equal weights are perfect, one dominant weight is terrible, zeros are ignored
+    from pypmc_b200.tools.convergence import perp, ess
+    assert perp(np.ones(10)) == pytest.approx(1.0) and ess(np.ones(10)) == pytest.approx(1.0)
+    w = np.array([1.0, 0.0, 0.0, 0.0])
+    assert perp(w) == pytest.approx(0.25) and ess(w) == pytest.approx(0.25)
+    w = np.array([0.2, 0.5, 0.1, 0.0, 1.7])
+    wn = w / w.sum()
+    assert perp(w) == pytest.approx(np.exp(-np.sum(wn[wn > 0] * np.log(wn[wn > 0]))) / 5)
+    assert ess(w) == pytest.approx(1.0 / (1.0 + np.mean((5 * wn - 1) ** 2)))
