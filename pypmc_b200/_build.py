@@ -42,8 +42,8 @@ def _compile(src: str, force: bool, hdr_mtime: float) -> str:
     if not force and os.path.exists(o) and os.path.getmtime(o) >= max(os.path.getmtime(s), hdr_mtime):
         return o
     log = subprocess.run([_nvcc(), *NVCC_FLAGS, "-c", s, "-o", o], capture_output=True, text=True)
-    with open(o[:-2] + ".ptxas.log", "w") as fh:
-        fh.write(log.stderr)
+    with open(o[:-2] + ".ptxas.log", "w") as fh:   # registers / spills / shared memory per kernel; compile times dropped
+        fh.write("".join(ln for ln in log.stderr.splitlines(True) if "Compile time" not in ln))
     if log.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s" % (src, log.stderr[-4000:]))
     return o
