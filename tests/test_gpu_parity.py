@@ -497,3 +497,48 @@ def test_empty_and_single_row_inputs(pm):
     assert one.shape == (1,) and one[0] == pytest.approx(mix.multi_evaluate(x)[0], rel=1e-14)
     wd = torch.from_numpy(sw).cuda()
     assert perp(wd) == pytest.approx(perp(sw), rel=1e-12) and ess(wd) == pytest.approx(ess(sw), rel=1e-12)
+
+
+def test_full_size_update_invariants(pm):
+    """Size-independent properties of the update path at N = 2e6 (the oracle would take minutes):
+    K2 is additive over row shards; VB responsibilities sum to one per row, sum_k N_k = N and the N_k-weighted
+    component means reproduce the data mean; a PMC update preserves sum alpha = 1 and the weighted data mean."""
+    import torch
+    from pypmc_b200 import _lib
+    from pypmc_b200.density.mixture import create_gaussian_mixture
+    from pypmc_b200.mix_adapt.pmc import gaussian_pmc, DeviceSamples
+    from pypmc_b200.mix_adapt.variational import GaussianInference
+    K, D, N = 32, 30, 2_000_000
+    means, covs, w, _, _ = _synth(K, D, 10, seed=31)
+    mix = create_gaussian_mixture(means, covs, w)
+    x = mix.propose_device(N, np.random.RandomState(2), seed=3)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    sw = torch.rand(N, dtype=torch.float64, device="cuda", generator=g) + 0.5
+    rho = torch.rand((N, K), dtype=torch.float64, device="cuda", generator=g)
+    ctx = _lib.Context.get()
+    F = 3 + D + D * (D + 1) // 2
+    shift = torch.zeros(D, dtype=torch.float64, device="cuda")
+
+    def stats(lo, hi):
+        out = torch.empty((K, F), dtype=torch.float64, device="cuda")
+        ctx.suffstats(x[lo:hi], hi - lo, D, D, shift, rho[lo:hi], None, K, K, sw[lo:hi], out)
+        return out
+    half = N // 2 + 333
+    whole, parts = stats(0, N), stats(0, half) + stats(half, N)
+    assert float(((whole - parts).abs() / whole.abs().clamp_min(1e-300)).max()) < 1e-11
+    # first-moment column against a plain float64 reduction
+    col = ((sw[:, None] * rho)[:, :4].T @ x).cpu().numpy()
+    np.testing.assert_allclose(whole[:4, 2:2 + D].cpu().numpy(), col, rtol=1e-11, atol=1e-6)
+
+    vb = GaussianInference(x, initial_guess=mix)
+    r = vb._r_dev
+    assert float((r.sum(dim=1) - 1.0).abs().max()) < 1e-12
+    assert vb.N_comp.sum() == pytest.approx(N, rel=1e-12)
+    data_mean = x.mean(dim=0).cpu().numpy()
+    np.testing.assert_allclose((vb.N_comp[:, None] * vb.x_mean_comp).sum(0) / N, data_mean, rtol=1e-10, atol=1e-12)
+
+    new = gaussian_pmc(DeviceSamples(x, sw), mix)
+    assert new.weights.sum() == pytest.approx(1.0, abs=1e-13)
+    wmean = ((sw[:, None] * x).sum(0) / sw.sum()).cpu().numpy()
+    mix_mean = (new.weights[:, None] * np.array([c.mu for c in new.components])).sum(0)
+    np.testing.assert_allclose(mix_mean, wmean, rtol=1e-10, atol=1e-12)
