@@ -542,3 +542,27 @@ def test_full_size_update_invariants(pm):
     wmean = ((sw[:, None] * x).sum(0) / sw.sum()).cpu().numpy()
     mix_mean = (new.weights[:, None] * np.array([c.mu for c in new.components])).sum(0)
     np.testing.assert_allclose(mix_mean, wmean, rtol=1e-10, atol=1e-12)
+
+
+def test_pmc_run_fused_likelihood_matches_two_launch_flow(pm, golden):
+    """PMC.run(fuse_likelihood=True) serves the bound and the next update's responsibilities from one K1 launch;
+    it must follow the reference flow (same iteration count on the fixture, same mixture to rounding)."""
+    from pypmc_b200.mix_adapt.pmc import PMC, gaussian_pmc
+    g = golden("gauss_small")
+    mix = _mix(pm, g)
+    runs = []
+    for fuse in (False, True):
+        p = PMC(g["x"], mix, weights=g["sample_weights"])
+        conv = p.run(iterations=3, fuse_likelihood=fuse)
+        runs.append((conv, p.density.weights.copy(), np.array([c.sigma for c in p.density.components]), p.log_likelihood()))
+    assert runs[0][0] == runs[1][0] == (None if int(g["pmc_run3_converged"]) < 0 else int(g["pmc_run3_converged"]))
+    np.testing.assert_allclose(runs[1][1], runs[0][1], rtol=1e-12)
+    assert mat_err(runs[1][2], runs[0][2]) < 1e-12
+    assert runs[1][3] == pytest.approx(runs[0][3], rel=1e-13)
+    np.testing.assert_allclose(runs[1][1], g["pmc_run3_weights"], rtol=1e-8)
+    # a pass computed ahead is never applied to a different mixture
+    p = PMC(g["x"], mix, weights=g["sample_weights"])
+    p.run(iterations=1, fuse_likelihood=True)
+    other = gaussian_pmc(p._device_samples, mix, weights=g["sample_weights"])       # not p.density: must recompute rho
+    ref = gaussian_pmc(g["x"], mix, weights=g["sample_weights"])
+    np.testing.assert_array_equal(other.weights, ref.weights)
