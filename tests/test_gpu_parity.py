@@ -566,3 +566,31 @@ def test_pmc_run_fused_likelihood_matches_two_launch_flow(pm, golden):
     other = gaussian_pmc(p._device_samples, mix, weights=g["sample_weights"])       # not p.density: must recompute rho
     ref = gaussian_pmc(g["x"], mix, weights=g["sample_weights"])
     np.testing.assert_array_equal(other.weights, ref.weights)
+
+
+def test_upload_and_pageable_staging(pm):
+    """Large host arrays go through the library's pinned staging (pmcb200_upload / the host pipeline): contents
+    must arrive bit for bit, for contiguous, row-strided and 1-d inputs, and results through pageable and pinned
+    buffers must be the same bits."""
+    import torch
+    from pypmc_b200 import _device as dev
+    from pypmc_b200.density.mixture import create_gaussian_mixture
+    rng = np.random.default_rng(8)
+    big = rng.normal(size=(700_001, 9))                                 # 50 MB: above the staging threshold
+    assert torch.equal(dev.to_device(big).cpu(), torch.from_numpy(big))
+    view = big[::2, :7]                                                  # row-strided
+    assert view.nbytes < dev._BIG_UPLOAD or torch.equal(dev.to_device(view).cpu(), torch.from_numpy(np.ascontiguousarray(view)))
+    wide = rng.normal(size=(900_000, 12))[:, :10]                        # 72 MB, padded rows
+    assert torch.equal(dev.to_device(wide).cpu(), torch.from_numpy(np.ascontiguousarray(wide)))
+    vec = rng.normal(size=5_000_000)
+    assert torch.equal(dev.to_device(vec).cpu(), torch.from_numpy(vec))
+    means, covs, w, _, _ = _synth(4, 9, 10, seed=5)
+    mix = create_gaussian_mixture(means, covs, w)
+    ind_a, ind_b = np.empty((len(big), 4)), torch.empty((len(big), 4), dtype=torch.float64, pin_memory=True)
+    xa = big
+    xb = torch.empty(big.shape, dtype=torch.float64, pin_memory=True)
+    xb.numpy()[:] = big
+    la = mix.multi_evaluate(xa, individual=ind_a)                        # pageable in, pageable out (staged both ways)
+    lb = mix.multi_evaluate(xb.numpy(), individual=ind_b.numpy())        # pinned in, pinned out (in place)
+    np.testing.assert_array_equal(la, lb)
+    np.testing.assert_array_equal(ind_a, ind_b.numpy())
