@@ -11,6 +11,8 @@
  *     (thread-local).  There is no CPU fallback: without a CUDA device every compute call fails.
  *   - `*_dev` pointers are device pointers on the context's device, `*_host` pointers are host memory
  *     (pinned memory makes the copies asynchronous and fast; pageable memory works).
+ *   - a context is bound to one device and is not thread-safe: one context per host thread (the Python mirror keeps
+ *     one per device and holds the GIL across calls); several contexts / processes may share a GPU.
  *   - all matrices are float64, row-major; `stream` is a cudaStream_t passed as void* (NULL = default).
  *   - N x K outputs have row stride k_out.
  */

@@ -28,7 +28,8 @@ int k1_tile_rows(int dp);   // samples per CTA tile for this DP (same for both f
     static_assert(FastCfg<DP>::TS == EvalCfg<DP>::TS, "both K1 forms must tile the samples alike");  \
     static_assert(FastCfg<DP>::NW <= PMC_MAX_WARPS && EvalCfg<DP>::NW <= PMC_MAX_WARPS, "partials"); \
     static_assert(FastCfg<DP>::SMEM_STAGED + 16 <= 227 * 1024, "staging does not fit");             \
-    static bool attr_set = false;                                                                     \
+    static PerDeviceFlag attr_flag;                                                                   \
+    bool& attr_set = attr_flag.here();                                                                \
     if (!attr_set) {                                                                                  \
       cudaError_t e = cudaFuncSetAttribute(k1_mixture_eval<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                            int(EvalCfg<DP>::SMEM_BYTES));                             \

@@ -100,6 +100,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 // ---------------------------------------------------------------------------------------------
 void set_last_error(const std::string& msg);
 
+// cudaFuncSetAttribute is per device: remember per device whether a kernel's shared-memory limit was raised
+struct PerDeviceFlag {
+  bool done[64] = {};
+  bool& here() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return done[(dev >= 0 && dev < 64) ? dev : 0];
+  }
+};
+
 #define PMC_CUDA_CHECK(expr)                                                                       \
   do {                                                                                             \
     cudaError_t _e = (expr);                                                                       \

@@ -383,7 +383,8 @@ int pmcb200_suffstats(pmcb200_ctx* c, const double* x, int64_t n, int64_t ldx, i
   const int gx = int(std::max<int64_t>(1, std::min<int64_t>(tiles, std::max(1, c->sm_count / gy))));
   if (int rc = ensure(c->ws, size_t(gx) * len * sizeof(double))) return rc;
   a.partial = static_cast<double*>(c->ws.p);
-  static bool attr_set = false;
+  static PerDeviceFlag attr_flag;
+  bool& attr_set = attr_flag.here();
   if (!attr_set) {
     PMC_CUDA_CHECK(cudaFuncSetAttribute(k2_suffstats, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
@@ -581,7 +582,8 @@ int pmcb200_mixture_propose(pmcb200_ctx* c, int64_t n, int d, int k, const doubl
   ProposeArgs a{n, ldx, d, k, means, chol, dofs, static_cast<const int64_t*>(c->pws.p), seed, index0, x, latent};
   const size_t smem = sizeof(double) * size_t(K3_THREADS) * (d | 1) + sizeof(int64_t) * size_t(k + 1) + 16;
   PMC_REQUIRE(smem <= 200 * 1024, "mixture_propose: too many components for the shared-memory table");
-  static bool attr_set = false;
+  static PerDeviceFlag attr_flag;
+  bool& attr_set = attr_flag.here();
   if (!attr_set) {
     PMC_CUDA_CHECK(cudaFuncSetAttribute(k3_propose, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
