@@ -30,7 +30,9 @@
 // mbarriers (full / empty), so the consumers never wait on global memory and there is no block-wide barrier
 // in the sample loop.
 // Each CTA writes one partial block; a second tiny kernel adds the partials in CTA order -- no floating-point
-// atomics, so results are reproducible run to run for a given grid.
+// atomics, so results are reproducible run to run for a given grid.  The default consumer form issues the update as
+// FP64 matrix instructions (DMMA, see the template note below); the DFMA register tile described here is kept
+// behind PMCB200_K2_FORM=dfma for comparison (13.4 ms vs 10.4 ms at N=1e7, K=32, D=30).
 #pragma once
 
 #include "pmc_common.cuh"
@@ -57,7 +59,10 @@ struct StatsArgs {
   int DP4;              // d+1 rounded up to a multiple of 4: row length of the staged samples
   int KP;               // k rounded up to a multiple of 16
   int LT;               // lane tiles = (KP/16) * (Bq + Lq)
-  int tn;               // samples per tile (multiple of 2)
+  int tn;               // samples per tile (multiple of 8)
+  int VS, YS;           // row strides (doubles) of the staged v and [y, 1] rows
+  int nFB;              // MMA form: feature blocks of 8 = ceil(F / 8)
+  int fchunks;          // MMA form: CTAs (gridDim.y direction) sharing the feature blocks
   double* partial;      // [gridDim.x, k, F+2]   (column 0 = A, column 1+f = Out[k,f], column F+1 = sum w rho ln gamma)
 };
 
@@ -76,21 +81,26 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // Stage layout (doubles): V [TN][KP] | Y [TN][DP4].  The producer warpgroup (88 registers) reads rho / gamma /
 // x / w rows from global memory, forms v = w rho gamma and yh = [x - shift, 1, 0...] and stores them; the two
 // consumer warpgroups (208 registers, setmaxnreg) only ever touch shared memory and the FP64 pipe.
+//
+// Consumer forms (template): CB == 0 -- the DFMA register tile described above.  CB > 0 -- the same rank-N update
+// issued as FP64 matrix instructions (mma.sync.m8n8k4.f64, SASS DMMA): a warp owns CB x FB tiles of 8 components x
+// 8 features, per 4 samples it loads CB A-fragments (v) and forms FB B-fragments (products of two [y, 1] entries)
+// and issues CB x FB DMMAs.  Why: a DFMA reads three 64-bit register operands and the register file delivers about
+// one per clock, which caps the DFMA form at 66-83 % of the pipe's peak (profiles/r01_operand_delivery.md); a
+// DMMA moves 256 FMAs with four operand registers per thread and runs at the full 37 TFLOP/s.
+template <int CB, int FB>
 __global__ void __launch_bounds__(K2_THREADS, 1) k2_suffstats(const StatsArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x;
-  const int D = a.d, KP = a.KP, DP4 = a.DP4, TN = a.tn;
+  const int D = a.d, KP = a.KP, DP4 = a.DP4, TN = a.tn, VS = a.VS, YS = a.YS;
   const bool has_g = a.gamma != nullptr;
-  const int stage_len = TN * (KP + DP4);
+  const int stage_len = TN * (VS + YS);
   double* stage0 = reinterpret_cast<double*>(smem_raw);
   double* shift_s = stage0 + K2_STAGES * stage_len;               // [DP4]
-  double* colsum = shift_s + DP4;                                 // gamma only: [4 producer warps][2][KP]
-  uint64_t* full = reinterpret_cast<uint64_t*>(colsum + (has_g ? 4 * 2 * KP : 0));
+  uint64_t* full = reinterpret_cast<uint64_t*>(shift_s + DP4);
   uint64_t* empty = full + K2_STAGES;
 
   for (int j = tid; j < DP4; j += K2_THREADS) shift_s[j] = (j < D) ? a.shift[j] : 0.0;
-  if (has_g)
-    for (int e = tid; e < 4 * 2 * KP; e += K2_THREADS) colsum[e] = 0.0;
   if (tid == 0) {
     for (int s = 0; s < K2_STAGES; ++s) {
       mbar_init(&full[s], K2_PRODUCERS);
@@ -108,13 +118,12 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_suffstats(const StatsArgs a)
     // =============================== producer warpgroup ===============================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
     const int pw = (tid - K2_CONSUMERS) >> 5, lane = tid & 31;
-    double* cs_a = colsum + pw * 2 * KP;
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int s = it % K2_STAGES;
       mbar_wait(&empty[s], uint32_t(((it / K2_STAGES) & 1) ^ 1));
       double* Vs = stage0 + s * stage_len;
-      double* Ys = Vs + TN * KP;
+      double* Ys = Vs + TN * VS;
       const int64_t row0 = tile * TN;
       const int rows = int((a.n - row0 < TN) ? (a.n - row0) : TN);
       if (KP <= 64 && DP4 <= 64) {
@@ -140,18 +149,9 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_suffstats(const StatsArgs a)
           for (int c = 0; c < 2; ++c) {
             const int kk = lane + 32 * c;                         // column of V and of Y handled by this lane
             if (kk < KP) {
-              double sa = 0.0, sl = 0.0;
 #pragma unroll
-              for (int u = 0; u < K2_PR; ++u) {
-                double v = rv[u][c] * w[u];
-                if (has_g) {
-                  sa += v;
-                  sl += (v != 0.0) ? v * log(gv[u][c]) : 0.0;     // feeds the dof condition, pmc.pyx:672-679
-                  v *= gv[u][c];
-                }
-                if (rb + u < TN) Vs[(rb + u) * KP + kk] = v;
-              }
-              if (has_g) { cs_a[kk] += sa; cs_a[KP + kk] += sl; }  // same thread every time: ordered, no race
+              for (int u = 0; u < K2_PR; ++u)
+                if (rb + u < TN) Vs[(rb + u) * VS + kk] = rv[u][c] * w[u] * gv[u][c];
             }
             if (kk < DP4) {
               const double sh = shift_s[kk];
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_suffstats(const StatsArgs a)
               for (int u = 0; u < K2_PR; ++u) {
                 double y = 0.0;
                 if (rb + u < rows) y = (kk < D) ? (xv[u][c] - sh) : ((kk == D) ? 1.0 : 0.0);
-                if (rb + u < TN) Ys[(rb + u) * DP4 + kk] = y;
+                if (rb + u < TN) Ys[(rb + u) * YS + kk] = y;
               }
             }
           }
@@ -177,18 +177,9 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_suffstats(const StatsArgs a)
               rv[u] = in ? __ldg(a.rho + (row0 + rb + u) * a.ld_rho + kk) : 0.0;
               gv[u] = (in && has_g) ? __ldg(a.gamma + (row0 + rb + u) * a.ld_rho + kk) : 1.0;
             }
-            double sa = 0.0, sl = 0.0;
   #pragma unroll
-            for (int u = 0; u < K2_PR; ++u) {
-              double v = rv[u] * w[u];
-              if (has_g) {
-                sa += v;
-                sl += (v != 0.0) ? v * log(gv[u]) : 0.0;        // feeds the dof condition, pmc.pyx:672-679
-                v *= gv[u];
-              }
-              if (rb + u < TN) Vs[(rb + u) * KP + kk] = v;
-            }
-            if (has_g) { cs_a[kk] += sa; cs_a[KP + kk] += sl; }  // same thread every time: ordered, no race
+            for (int u = 0; u < K2_PR; ++u)
+              if (rb + u < TN) Vs[(rb + u) * VS + kk] = rv[u] * w[u] * gv[u];
           }
           for (int jj = lane; jj < DP4; jj += 32) {
             double xv[K2_PR];
@@ -200,113 +191,236 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_suffstats(const StatsArgs a)
             for (int u = 0; u < K2_PR; ++u) {
               double y = 0.0;
               if (rb + u < rows) y = (jj < D) ? (xv[u] - sh) : ((jj == D) ? 1.0 : 0.0);
-              if (rb + u < TN) Ys[(rb + u) * DP4 + jj] = y;
+              if (rb + u < TN) Ys[(rb + u) * YS + jj] = y;
             }
           }
         }
       }
       mbar_arrive(&full[s]);                                   // release: this thread's stores are visible to waiters
     }
-    // ---- column sums (gamma) / zero column (no gamma), CTA row 0 only ----
-    if (blockIdx.y == 0) {
-      asm volatile("bar.sync 1, %0;" ::"n"(K2_PRODUCERS) : "memory");   // producers only
-      const int ptid = tid - K2_CONSUMERS;
-      for (int k = ptid; k < a.k; k += K2_PRODUCERS) {
-        if (has_g) {
-          double sa = 0.0, sl = 0.0;
-          for (int wv = 0; wv < 4; ++wv) { sa += colsum[wv * 2 * KP + k]; sl += colsum[wv * 2 * KP + KP + k]; }
-          out[size_t(k) * ldp] = sa;
-          out[size_t(k) * ldp + a.F + 1] = sl;
-        } else {
-          out[size_t(k) * ldp + a.F + 1] = 0.0;
-        }
-      }
-    }
+    // column 0 (A) with gamma and column F+1 (L) are written by k2_colsums / k2_colsums_final
     return;
   }
 
   // ================================= consumer warpgroups =================================
   asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
-  // ---- this thread's lane tile ----
-  const int t = blockIdx.y * K2_CONSUMERS + tid;
-  const bool active = t < a.LT;
-  const int tt = active ? t : 0;
-  const int per_group = a.Bq + a.Lq;
-  const int kg = tt / per_group, b = tt - kg * per_group;
-  const bool lin = b >= a.Bq;                     // linear tile: entries 4q .. 4q+3 of [y, 1]
-  int r = 0, p = 0;
-  if (!lin) {
-    r = int((sqrt(8.0 * b + 1.0) - 1.0) * 0.5);
-    while ((r + 1) * (r + 2) / 2 <= b) ++r;
-    while (r * (r + 1) / 2 > b) --r;
-    p = b - r * (r + 1) / 2;
-  }
-  const int off_a = lin ? 4 * (b - a.Bq) + 2 : 2 * r;    // second pair (linear) / row pair (quadratic)
-  const int off_b = lin ? 4 * (b - a.Bq) : 2 * p;        // first pair (linear) / column pair (quadratic)
-
-  double acc[K2_TK][4];
+  if constexpr (CB > 0) {
+    const int warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tq = lane & 3;            // fragment coordinates: A row / B col / C row = g, k index = tq
+    const int chunk_f = blockIdx.y % a.fchunks, chunk_c = blockIdx.y / a.fchunks;
+    const int fb_first = (chunk_f * (K2_CONSUMERS / 32) + warp) * FB;     // first feature block of this warp
+    const int cb_first = chunk_c * CB, cb_total = KP / 8;
+    const int nfb_w = max(0, min(FB, a.nFB - fb_first));
+    // feature f -> the two entries of [y, 1, 0] whose product it is: f = 0: 1*1 (B_k); 1..D: y_i * 1 (m_k); then the
+    // lower triangle of y y^T row-major; beyond F: the zero column D+1
+    int off_i[FB], off_j[FB];
 #pragma unroll
-  for (int i = 0; i < K2_TK; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-
-  int it = 0;
-  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-    const int s = it % K2_STAGES;
-    mbar_wait(&full[s], uint32_t((it / K2_STAGES) & 1));
-    const double* Vs = stage0 + s * stage_len;
-    const double* Ys = Vs + TN * KP;
-    // ---- rank-TN update of the register tile ----
-    const double* vp = Vs + kg * K2_TK;
-    const double* yr = Ys + off_a;
-    const double* yp = Ys + off_b;
-#pragma unroll 2
-    for (int n = 0; n < TN; ++n) {
-      const double2 ya = *reinterpret_cast<const double2*>(yr + n * DP4);
-      const double2 yb = *reinterpret_cast<const double2*>(yp + n * DP4);
-      const double f0 = lin ? yb.x : ya.x * yb.x, f1 = lin ? yb.y : ya.x * yb.y;
-      const double f2 = lin ? ya.x : ya.y * yb.x, f3 = lin ? ya.y : ya.y * yb.y;
-#pragma unroll
-      for (int c = 0; c < K2_TK / 2; ++c) {
-        const double2 v = *reinterpret_cast<const double2*>(vp + n * KP + 2 * c);
-        acc[2 * c][0] = fma(v.x, f0, acc[2 * c][0]);
-        acc[2 * c][1] = fma(v.x, f1, acc[2 * c][1]);
-        acc[2 * c][2] = fma(v.x, f2, acc[2 * c][2]);
-        acc[2 * c][3] = fma(v.x, f3, acc[2 * c][3]);
-        // snake order: consecutive DFMAs share v or f alternately, so each needs one new register operand plus its
-        // accumulator -- the register file delivers ~1 64-bit warp operand per clock (scripts/ubench/dfma_snake.cu)
-        acc[2 * c + 1][3] = fma(v.y, f3, acc[2 * c + 1][3]);
-        acc[2 * c + 1][2] = fma(v.y, f2, acc[2 * c + 1][2]);
-        acc[2 * c + 1][1] = fma(v.y, f1, acc[2 * c + 1][1]);
-        acc[2 * c + 1][0] = fma(v.y, f0, acc[2 * c + 1][0]);
+    for (int fb = 0; fb < FB; ++fb) {
+      const int f = (fb_first + fb) * 8 + g;
+      int oi = D + 1, oj = D + 1;
+      if (f == 0) { oi = D; oj = D; }
+      else if (f <= D) { oi = f - 1; oj = D; }
+      else if (f < a.F) {
+        const int t = f - 1 - D;
+        int r = int((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+        while ((r + 1) * (r + 2) / 2 <= t) ++r;
+        while (r * (r + 1) / 2 > t) --r;
+        oi = r; oj = t - r * (r + 1) / 2;
       }
+      off_i[fb] = oi; off_j[fb] = oj;
     }
-    mbar_arrive(&empty[s]);                                     // the producer may refill this stage
-  }
-
-  // ---- write this CTA's partial block ----
-  if (active) {
+    // component blocks beyond KP/8 (cb_total not a multiple of CB) re-read block 0 and are dropped at the end
+    int cb_off[CB];
 #pragma unroll
-    for (int c = 0; c < K2_TK; ++c) {
-      const int k = kg * K2_TK + c;
+    for (int cb = 0; cb < CB; ++cb) cb_off[cb] = (cb_first + cb < cb_total) ? cb * 8 : -cb_first * 8;
+    double acc[CB][FB][2];
+#pragma unroll
+    for (int cb = 0; cb < CB; ++cb)
+#pragma unroll
+      for (int fb = 0; fb < FB; ++fb) { acc[cb][fb][0] = 0.0; acc[cb][fb][1] = 0.0; }
+
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int s = it % K2_STAGES;
+      mbar_wait(&full[s], uint32_t((it / K2_STAGES) & 1));
+      const double* Vs = stage0 + s * stage_len;
+      const double* Ys = Vs + TN * VS;
+      if (nfb_w > 0) {
+        // no branch inside the step: feature blocks beyond the warp's share multiply the zero column, so every
+        // load of a step can be issued before its first DMMA and the 32 DMMAs go back to back
+#pragma unroll 2
+        for (int n0 = 0; n0 < TN; n0 += 4) {
+          const double* vrow = Vs + (n0 + tq) * VS + cb_first * 8 + g;
+          const double* yrow = Ys + (n0 + tq) * YS;
+          double av[CB], bv[FB];
+#pragma unroll
+          for (int cb = 0; cb < CB; ++cb) av[cb] = vrow[cb_off[cb]];
+#pragma unroll
+          for (int fb = 0; fb < FB; ++fb) bv[fb] = yrow[off_i[fb]] * yrow[off_j[fb]];
+#pragma unroll
+          for (int fb = 0; fb < FB; ++fb)
+#pragma unroll
+            for (int cb = 0; cb < CB; ++cb)
+              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                           : "+d"(acc[cb][fb][0]), "+d"(acc[cb][fb][1])
+                           : "d"(av[cb]), "d"(bv[fb]));
+        }
+      }
+      mbar_arrive(&empty[s]);                                   // the producer may refill this stage
+    }
+    // ---- write this CTA's partial block: lane holds Out[8 cb + g][8 fb + 2 tq + e] ----
+#pragma unroll
+    for (int cb = 0; cb < CB; ++cb) {
+      const int k = (cb_first + cb) * 8 + g;
       if (k >= a.k) continue;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        int f;
-        if (lin) {
-          const int j = off_b + q;                    // entry of [y, 1]
-          if (j > D) continue;                        // padding
-          f = (j == D) ? 0 : 1 + j;                   // B_k / m_k
-        } else {
-          const int i = 2 * r + (q >> 1), j = 2 * p + (q & 1);
-          if (j > i || i >= D) continue;              // duplicate above the diagonal / padding (odd D)
-          f = 1 + D + i * (i + 1) / 2 + j;            // second moments, lower triangle row-major
+      for (int fb = 0; fb < FB; ++fb) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int f = (fb_first + fb) * 8 + 2 * tq + e;
+          if (fb >= nfb_w || f >= a.F) continue;
+          out[size_t(k) * ldp + 1 + f] = acc[cb][fb][e];
+          if (f == 0 && !has_g) out[size_t(k) * ldp] = acc[cb][fb][e];   // A == B without gamma
         }
-        out[size_t(k) * ldp + 1 + f] = acc[c][q];
-        if (f == 0 && !has_g) out[size_t(k) * ldp] = acc[c][q];   // A == B without gamma
+      }
+    }
+    return;
+  } else {
+    // ---- this thread's lane tile ----
+    const int t = blockIdx.y * K2_CONSUMERS + tid;
+    const bool active = t < a.LT;
+    const int tt = active ? t : 0;
+    const int per_group = a.Bq + a.Lq;
+    const int kg = tt / per_group, b = tt - kg * per_group;
+    const bool lin = b >= a.Bq;                     // linear tile: entries 4q .. 4q+3 of [y, 1]
+    int r = 0, p = 0;
+    if (!lin) {
+      r = int((sqrt(8.0 * b + 1.0) - 1.0) * 0.5);
+      while ((r + 1) * (r + 2) / 2 <= b) ++r;
+      while (r * (r + 1) / 2 > b) --r;
+      p = b - r * (r + 1) / 2;
+    }
+    const int off_a = lin ? 4 * (b - a.Bq) + 2 : 2 * r;    // second pair (linear) / row pair (quadratic)
+    const int off_b = lin ? 4 * (b - a.Bq) : 2 * p;        // first pair (linear) / column pair (quadratic)
+
+    double acc[K2_TK][4];
+  #pragma unroll
+    for (int i = 0; i < K2_TK; ++i)
+  #pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int s = it % K2_STAGES;
+      mbar_wait(&full[s], uint32_t((it / K2_STAGES) & 1));
+      const double* Vs = stage0 + s * stage_len;
+      const double* Ys = Vs + TN * VS;
+      // ---- rank-TN update of the register tile ----
+      const double* vp = Vs + kg * K2_TK;
+      const double* yr = Ys + off_a;
+      const double* yp = Ys + off_b;
+  #pragma unroll 2
+      for (int n = 0; n < TN; ++n) {
+        const double2 ya = *reinterpret_cast<const double2*>(yr + n * YS);
+        const double2 yb = *reinterpret_cast<const double2*>(yp + n * YS);
+        const double f0 = lin ? yb.x : ya.x * yb.x, f1 = lin ? yb.y : ya.x * yb.y;
+        const double f2 = lin ? ya.x : ya.y * yb.x, f3 = lin ? ya.y : ya.y * yb.y;
+  #pragma unroll
+        for (int c = 0; c < K2_TK / 2; ++c) {
+          const double2 v = *reinterpret_cast<const double2*>(vp + n * VS + 2 * c);
+          acc[2 * c][0] = fma(v.x, f0, acc[2 * c][0]);
+          acc[2 * c][1] = fma(v.x, f1, acc[2 * c][1]);
+          acc[2 * c][2] = fma(v.x, f2, acc[2 * c][2]);
+          acc[2 * c][3] = fma(v.x, f3, acc[2 * c][3]);
+          // snake order: consecutive DFMAs share v or f alternately, so each needs one new register operand plus its
+          // accumulator -- the register file delivers ~1 64-bit warp operand per clock (scripts/ubench/dfma_snake.cu)
+          acc[2 * c + 1][3] = fma(v.y, f3, acc[2 * c + 1][3]);
+          acc[2 * c + 1][2] = fma(v.y, f2, acc[2 * c + 1][2]);
+          acc[2 * c + 1][1] = fma(v.y, f1, acc[2 * c + 1][1]);
+          acc[2 * c + 1][0] = fma(v.y, f0, acc[2 * c + 1][0]);
+        }
+      }
+      mbar_arrive(&empty[s]);                                     // the producer may refill this stage
+    }
+
+    // ---- write this CTA's partial block ----
+    if (active) {
+  #pragma unroll
+      for (int c = 0; c < K2_TK; ++c) {
+        const int k = kg * K2_TK + c;
+        if (k >= a.k) continue;
+  #pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          int f;
+          if (lin) {
+            const int j = off_b + q;                    // entry of [y, 1]
+            if (j > D) continue;                        // padding
+            f = (j == D) ? 0 : 1 + j;                   // B_k / m_k
+          } else {
+            const int i = 2 * r + (q >> 1), j = 2 * p + (q & 1);
+            if (j > i || i >= D) continue;              // duplicate above the diagonal / padding (odd D)
+            f = 1 + D + i * (i + 1) / 2 + j;            // second moments, lower triangle row-major
+          }
+          out[size_t(k) * ldp + 1 + f] = acc[c][q];
+          if (f == 0 && !has_g) out[size_t(k) * ldp] = acc[c][q];   // A == B without gamma
+        }
       }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Column sums that go with gamma (Student-t): A_k = sum_n w_n rho_nk and L_k = sum_n w_n rho_nk ln(gamma_nk)
+// (the N-sized part of the dof condition, pmc.pyx:654-691).  A streaming pass of its own: in the producer warps of
+// k2_suffstats the logarithm cost 2 ms of 8 at C4 (4 warps per SM, latency-bound); here every SM runs 8 full CTAs.
+// Thread t owns column t % kc and rows t / kc, t / kc + 256 / kc, ...; per-CTA partials, summed in CTA order.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k2_colsums(const double* __restrict__ rho, const double* __restrict__ gamma,
+                                                  const double* __restrict__ sw, int64_t n, int k, int ld_rho, int kc,
+                                                  double* __restrict__ partial /* [grid][2][k] */) {
+  __shared__ double red[2][256];
+  const int tid = threadIdx.x, rows_per_pass = 256 / kc, r_off = tid / kc;
+  for (int k0 = 0; k0 < k; k0 += kc) {
+    const int kk = k0 + tid % kc;
+    double sa = 0.0, sl = 0.0;
+    if (kk < k) {
+      for (int64_t r = int64_t(blockIdx.x) * rows_per_pass + r_off; r < n; r += int64_t(gridDim.x) * rows_per_pass) {
+        double v = __ldg(rho + r * ld_rho + kk);
+        if (sw) v *= __ldg(sw + r);
+        const double gm = __ldg(gamma + r * ld_rho + kk);
+        sa += v;
+        sl += (v != 0.0) ? v * log(gm) : 0.0;
+      }
+    }
+    red[0][tid] = sa;
+    red[1][tid] = sl;
+    __syncthreads();
+    if (tid < kc && kk < k) {
+      double a0 = 0.0, l0 = 0.0;
+      for (int u = tid; u < 256; u += kc) { a0 += red[0][u]; l0 += red[1][u]; }     // fixed order
+      partial[(size_t(blockIdx.x) * 2 + 0) * k + kk] = a0;
+      partial[(size_t(blockIdx.x) * 2 + 1) * k + kk] = l0;
+    }
+    __syncthreads();
+  }
+}
+
+// out[k][0] = A_k, out[k][F+1] = L_k from the per-CTA partials (CTA order); L_k = 0 without gamma
+__global__ void k2_colsums_final(const double* __restrict__ partial, int nblocks, int k, int ldp, int F, int has_gamma,
+                                 double* __restrict__ out) {
+  const int kk = blockIdx.x * blockDim.x + threadIdx.x;
+  if (kk >= k) return;
+  if (!has_gamma) {
+    out[size_t(kk) * ldp + F + 1] = 0.0;
+    return;
+  }
+  double a0 = 0.0, l0 = 0.0;
+  for (int b = 0; b < nblocks; ++b) {
+    a0 += partial[(size_t(b) * 2 + 0) * k + kk];
+    l0 += partial[(size_t(b) * 2 + 1) * k + kk];
+  }
+  out[size_t(kk) * ldp] = a0;
+  out[size_t(kk) * ldp + F + 1] = l0;
 }
 
 // out[e] = sum_b partial[b][e], b ascending (fixed order)

@@ -93,6 +93,7 @@ struct pmcb200_ctx {
   DevBuf ws;              // partial sums of K2 / microbenchmark scratch
   DevBuf k1ws;            // K1: derived records, shift, flag, per-warp partial sums (device-pointer entry point)
   DevBuf pws;             // K3: block starts
+  DevBuf cws;             // K2: per-CTA partial column sums (gamma)
   DevBuf k1row;           // K1: per-row (max, 1/denominator) handed from k1_fast_eval to k1_finish
   cudaStream_t copy_stream[2] = {nullptr, nullptr};
   // host pipeline: per-slot device buffers
@@ -203,7 +204,7 @@ int pmcb200_create(int device, pmcb200_ctx** out) {
 int pmcb200_destroy(pmcb200_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
-  DevBuf* all[] = {&c->ws, &c->k1ws, &c->k1row, &c->pws, &c->hrec, &c->hcols};
+  DevBuf* all[] = {&c->ws, &c->k1ws, &c->k1row, &c->pws, &c->cws, &c->hrec, &c->hcols};
   for (DevBuf* b : all)
     if (b->p) cudaFree(b->p);
   for (int i = 0; i < 2; ++i) {
@@ -367,13 +368,32 @@ int pmcb200_suffstats(pmcb200_ctx* c, const double* x, int64_t n, int64_t ldx, i
   a.P0 = (d + 1) / 2;
   a.Bq = a.P0 * (a.P0 + 1) / 2;
   a.Lq = (d + 4) / 4;
-  a.DP4 = a.Lq * 4;
   a.KP = ((k + K2_TK - 1) / K2_TK) * K2_TK;
   a.LT = (a.KP / K2_TK) * (a.Bq + a.Lq);
-  // lane tiles -> CTAs of 8 consumer warps; gy CTAs share the same samples when one CTA cannot hold every tile
-  const int gy = (a.LT + K2_CONSUMERS - 1) / K2_CONSUMERS;
-  const size_t per_row = sizeof(double) * (size_t(a.KP) + a.DP4);
-  const size_t fixed = sizeof(double) * (a.DP4 + (gamma ? size_t(8) * a.KP : 0)) + 2 * K2_STAGES * sizeof(uint64_t) + 128;
+  // consumer form: FP64 matrix instructions (default) or the DFMA register tile (PMCB200_K2_FORM=dfma)
+  static const char* form_env = getenv("PMCB200_K2_FORM");
+  const bool mma = !(form_env && std::string(form_env) == "dfma");
+  int gy, cbw = 0, fbw = 0;
+  if (mma) {
+    const int cb_total = a.KP / 8;                       // component blocks of 8 (KP is a multiple of 16)
+    cbw = (cb_total <= 2) ? 2 : (cb_total <= 4) ? 4 : 8; // per-warp tile CB x FB with CB * FB = 32 C tiles (64 accumulators)
+    fbw = 32 / cbw;
+    a.nFB = (F + 7) / 8;
+    a.fchunks = (a.nFB + (K2_CONSUMERS / 32) * fbw - 1) / ((K2_CONSUMERS / 32) * fbw);
+    gy = a.fchunks * ((cb_total + cbw - 1) / cbw);
+    a.DP4 = ((d + 2 + 3) / 4) * 4;                       // [y, 1, 0...]: always at least one zero column (index d+1)
+    a.VS = a.KP + 4;                                     // row strides = 4 (mod 16) doubles: the 8 x 4 fragment loads of a
+    a.YS = ((a.DP4 + 11) / 16) * 16 + 4;                 // half-warp then touch 16 different 8-byte banks
+  } else {
+    a.nFB = 0;
+    a.fchunks = 1;
+    gy = (a.LT + K2_CONSUMERS - 1) / K2_CONSUMERS;       // lane tiles -> CTAs of 8 consumer warps
+    a.DP4 = a.Lq * 4;
+    a.VS = a.KP;
+    a.YS = a.DP4;
+  }
+  const size_t per_row = sizeof(double) * (size_t(a.VS) + a.YS);
+  const size_t fixed = sizeof(double) * a.DP4 + 2 * K2_STAGES * sizeof(uint64_t) + 128;
   int tn = int((size_t(210) * 1024 - fixed) / (K2_STAGES * per_row));
   tn = std::min(96, tn) & ~7;
   PMC_REQUIRE(tn >= 8, "suffstats: K and D too large for the shared-memory pipeline");
@@ -383,17 +403,40 @@ int pmcb200_suffstats(pmcb200_ctx* c, const double* x, int64_t n, int64_t ldx, i
   const int gx = int(std::max<int64_t>(1, std::min<int64_t>(tiles, std::max(1, c->sm_count / gy))));
   if (int rc = ensure(c->ws, size_t(gx) * len * sizeof(double))) return rc;
   a.partial = static_cast<double*>(c->ws.p);
-  static PerDeviceFlag attr_flag;
-  bool& attr_set = attr_flag.here();
-  if (!attr_set) {
-    PMC_CUDA_CHECK(cudaFuncSetAttribute(k2_suffstats, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
-  k2_suffstats<<<dim3(gx, gy), K2_THREADS, smem, st>>>(a);
-  PMC_CUDA_CHECK(cudaGetLastError());
+  auto launch = [&](auto kernel, PerDeviceFlag& flag) -> int {
+    bool& attr_set = flag.here();
+    if (!attr_set) {
+      PMC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_set = true;
+    }
+    kernel<<<dim3(gx, gy), K2_THREADS, smem, st>>>(a);
+    PMC_CUDA_CHECK(cudaGetLastError());
+    return 0;
+  };
+  static PerDeviceFlag f0, f2, f4, f8;
+  int rc;
+  if (!mma) rc = launch(k2_suffstats<0, 1>, f0);
+  else if (cbw == 2) rc = launch(k2_suffstats<2, 16>, f2);
+  else if (cbw == 4) rc = launch(k2_suffstats<4, 8>, f4);
+  else rc = launch(k2_suffstats<8, 4>, f8);
+  if (rc) return rc;
   k2_reduce_partials<<<unsigned((len + 255) / 256), 256, 0, st>>>(a.partial, gx, len, out);
   PMC_CUDA_CHECK(cudaGetLastError());
   c->launches += 2;
+  // columns 0 (A, with gamma) and F+1 (L) of the rows: a streaming pass of its own (k2_colsums)
+  const int cgrid = gamma ? int(std::min<int64_t>(int64_t(c->sm_count) * 8, std::max<int64_t>(1, n / 64))) : 0;
+  if (gamma) {
+    int kc = 1;
+    while (kc < k && kc < 256) kc <<= 1;
+    if (int rc2 = ensure(c->cws, size_t(cgrid) * 2 * k * sizeof(double))) return rc2;
+    k2_colsums<<<cgrid, 256, 0, st>>>(rho, gamma, weights, n, k, ld_rho, kc, static_cast<double*>(c->cws.p));
+    PMC_CUDA_CHECK(cudaGetLastError());
+    c->launches++;
+  }
+  k2_colsums_final<<<unsigned((k + 127) / 128), 128, 0, st>>>(static_cast<const double*>(c->cws.p), cgrid, k, F + 2, F,
+                                                               gamma ? 1 : 0, out);
+  PMC_CUDA_CHECK(cudaGetLastError());
+  c->launches++;
   return 0;
 }
 
