@@ -63,6 +63,7 @@ struct StatsArgs {
   int VS, YS;           // row strides (doubles) of the staged v and [y, 1] rows
   int nFB;              // MMA form: feature blocks of 8 = ceil(F / 8)
   int fchunks;          // MMA form: CTAs (gridDim.y direction) sharing the feature blocks
+  int fbw;              // MMA form: feature blocks per warp (= template FB)
   double* partial;      // [gridDim.x, k, F+2]   (column 0 = A, column 1+f = Out[k,f], column F+1 = sum w rho ln gamma)
 };
 

@@ -376,10 +376,20 @@ int pmcb200_suffstats(pmcb200_ctx* c, const double* x, int64_t n, int64_t ldx, i
   int gy, cbw = 0, fbw = 0;
   if (mma) {
     const int cb_total = a.KP / 8;                       // component blocks of 8 (KP is a multiple of 16)
-    cbw = (cb_total <= 2) ? 2 : (cb_total <= 4) ? 4 : 8; // per-warp tile CB x FB with CB * FB = 32 C tiles (64 accumulators)
-    fbw = 32 / cbw;
+    cbw = (cb_total <= 2) ? 2 : (cb_total <= 4) ? 4 : 8; // per-warp tile CB x FB, at most 32 C tiles (64 accumulators)
     a.nFB = (F + 7) / 8;
-    a.fchunks = (a.nFB + (K2_CONSUMERS / 32) * fbw - 1) / ((K2_CONSUMERS / 32) * fbw);
+    const int nw = K2_CONSUMERS / 32, fb_max = 32 / cbw;
+    a.fchunks = (a.nFB + nw * fb_max - 1) / (nw * fb_max);
+    const int need = (a.nFB + nw * a.fchunks - 1) / (nw * a.fchunks);   // feature blocks per warp, spread evenly
+    // instantiated FB values per CB (the smallest one >= need is used; blocks beyond the warp's share are zero work
+    // that is still issued, so a tight FB matters: D=40 gives 108 blocks = 13.5 per warp -> FB 14, not 16)
+    static const int fb2[] = {2, 4, 6, 8, 10, 12, 14, 16}, fb4[] = {1, 2, 3, 4, 5, 6, 7, 8}, fb8[] = {1, 2, 3, 4};
+    const int* tab = (cbw == 2) ? fb2 : (cbw == 4) ? fb4 : fb8;
+    const int ntab = (cbw == 2) ? 8 : (cbw == 4) ? 8 : 4;
+    fbw = tab[ntab - 1];
+    for (int i = 0; i < ntab; ++i)
+      if (tab[i] >= need) { fbw = tab[i]; break; }
+    a.fbw = fbw;
     gy = a.fchunks * ((cb_total + cbw - 1) / cbw);
     a.DP4 = ((d + 2 + 3) / 4) * 4;                       // [y, 1, 0...]: always at least one zero column (index d+1)
     a.VS = a.KP + 4;                                     // row strides = 4 (mod 16) doubles: the 8 x 4 fragment loads of a
@@ -387,6 +397,7 @@ int pmcb200_suffstats(pmcb200_ctx* c, const double* x, int64_t n, int64_t ldx, i
   } else {
     a.nFB = 0;
     a.fchunks = 1;
+    a.fbw = 0;
     gy = (a.LT + K2_CONSUMERS - 1) / K2_CONSUMERS;       // lane tiles -> CTAs of 8 consumer warps
     a.DP4 = a.Lq * 4;
     a.VS = a.KP;
@@ -413,12 +424,17 @@ int pmcb200_suffstats(pmcb200_ctx* c, const double* x, int64_t n, int64_t ldx, i
     PMC_CUDA_CHECK(cudaGetLastError());
     return 0;
   };
-  static PerDeviceFlag f0, f2, f4, f8;
-  int rc;
-  if (!mma) rc = launch(k2_suffstats<0, 1>, f0);
-  else if (cbw == 2) rc = launch(k2_suffstats<2, 16>, f2);
-  else if (cbw == 4) rc = launch(k2_suffstats<4, 8>, f4);
-  else rc = launch(k2_suffstats<8, 4>, f8);
+  static PerDeviceFlag flags[32];
+  int rc = 2;
+  if (!mma) rc = launch(k2_suffstats<0, 1>, flags[0]);
+#define PMC_K2_CASE(CBV, FBV, IDX) else if (cbw == CBV && fbw == FBV) rc = launch(k2_suffstats<CBV, FBV>, flags[IDX]);
+  PMC_K2_CASE(2, 2, 1) PMC_K2_CASE(2, 4, 2) PMC_K2_CASE(2, 6, 3) PMC_K2_CASE(2, 8, 4) PMC_K2_CASE(2, 10, 5)
+  PMC_K2_CASE(2, 12, 6) PMC_K2_CASE(2, 14, 7) PMC_K2_CASE(2, 16, 8)
+  PMC_K2_CASE(4, 1, 9) PMC_K2_CASE(4, 2, 10) PMC_K2_CASE(4, 3, 11) PMC_K2_CASE(4, 4, 12) PMC_K2_CASE(4, 5, 13)
+  PMC_K2_CASE(4, 6, 14) PMC_K2_CASE(4, 7, 15) PMC_K2_CASE(4, 8, 16)
+  PMC_K2_CASE(8, 1, 17) PMC_K2_CASE(8, 2, 18) PMC_K2_CASE(8, 3, 19) PMC_K2_CASE(8, 4, 20)
+#undef PMC_K2_CASE
+  PMC_REQUIRE(rc != 2, "suffstats: no kernel instantiation for this tile shape");
   if (rc) return rc;
   k2_reduce_partials<<<unsigned((len + 255) / 256), 256, 0, st>>>(a.partial, gx, len, out);
   PMC_CUDA_CHECK(cudaGetLastError());
