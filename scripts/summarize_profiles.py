@@ -82,7 +82,7 @@ def summarize_rep(rep, tag, traffic_for=None):
         d = dict(zip(hdr, r))
         u = dict(zip(hdr, units))
         kname = d["Kernel Name"]
-        short = kname.split("(")[0].replace("void ", "").replace("pmc::", "").replace("<", "_").replace(">", "").replace("(int)", "")
+        short = kname.split("(")[0].replace("void ", "").replace("pmc::", "").replace("<", "_").replace(">", "").replace("(int)", "").replace(", ", "x")
         lines = ["# ncu --set full: %s" % kname, "",
                  "Source: `gpurun_out/%s` (scratch), captured with `--clock-control none --import-source on`; one launch."
                  % os.path.basename(rep), "", "| metric | value | unit |", "|---|---|---|"]
