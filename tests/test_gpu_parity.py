@@ -7,6 +7,7 @@
 Tolerance (BASELINE.json north_star): 1e-10 relative, float64.  Covariance-type outputs use the
 max-norm metric of SURVEY 8c (``mat_err``).  Needs a B200: ``pytest -m gpu``.
 """
+import os
 import numpy as np
 import pytest
 
@@ -594,3 +595,39 @@ def test_upload_and_pageable_staging(pm):
     lb = mix.multi_evaluate(xb.numpy(), individual=ind_b.numpy())        # pinned in, pinned out (in place)
     np.testing.assert_array_equal(la, lb)
     np.testing.assert_array_equal(ind_a, ind_b.numpy())
+
+
+def test_k2_dfma_form_agrees_with_default(pm, tmp_path):
+    """The DFMA register-tile form of K2 (PMCB200_K2_FORM=dfma, kept for comparison with the default FP64
+    matrix-instruction form) must produce the same statistics to rounding.  The form is fixed per process, so the
+    DFMA run happens in a child process."""
+    import subprocess
+    import sys
+    import torch
+    from conftest import ROOT
+    from pypmc_b200 import _lib
+    script = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+from pypmc_b200 import _lib
+rng = np.random.default_rng(12)
+res = {}
+for (K, D, N, use_g) in [(32, 30, 5003, False), (16, 40, 3001, True), (70, 9, 2000, False), (3, 2, 100, True)]:
+    x = rng.normal(size=(N, D)) + 1.0
+    rho = rng.uniform(size=(N, K)); gam = rng.uniform(0.5, 2.0, size=(N, K)) if use_g else None
+    w = rng.uniform(0.5, 1.5, size=N); shift = rng.normal(size=D)
+    out = torch.empty((K, 3 + D + D * (D + 1) // 2), dtype=torch.float64, device="cuda")
+    tod = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    _lib.Context.get().suffstats(tod(x), N, D, D, tod(shift), tod(rho), tod(gam), K, K, tod(w), out)
+    res["%%d_%%d" %% (K, D)] = out.cpu().numpy()
+np.savez(sys.argv[1], **res)
+''' % ROOT
+    outs = {}
+    for form in ("mma", "dfma"):
+        path = str(tmp_path / (form + ".npz"))
+        env = dict(os.environ, PMCB200_K2_FORM=form)
+        subprocess.run([sys.executable, "-c", script, path], check=True, env=env, timeout=300)
+        outs[form] = dict(np.load(path))
+    for key in outs["mma"]:
+        a, b = outs["mma"][key], outs["dfma"][key]
+        assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-9)) < 1e-11, key
