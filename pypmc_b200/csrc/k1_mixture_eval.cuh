@@ -1,5 +1,9 @@
-// k1_mixture_eval.cuh -- K1: fused per-sample x per-component log-pdf + mixture log-sum-exp +
-// responsibilities, float64, sm_100a.
+// k1_mixture_eval.cuh -- K1, exact-difference form: fused per-sample x per-component log-pdf + mixture
+// log-sum-exp + responsibilities, float64, sm_100a.  This is the FALLBACK of K1: the form that normally runs is
+// k1_fast_eval.cuh; this one takes over (device-side flag from k1_prepare, no host synchronisation) when a component
+// lies so far from the common shift that the fast form's rounding bound D eps max|b| would exceed the contract.
+// It forms y = x - mu_k per component exactly like the reference does and was the first K1 of round 1
+// (16.2 ms at N=1e7, K=32, D=30 against 12.9 ms for the fast form).
 //
 // Replaces (reference loops, /root/reference/pypmc):
 //   Gauss.multi_evaluate            density/gauss.pyx:146-151      (bilinear_sym tools/_linalg.pyx:10-39)
