@@ -46,6 +46,34 @@ class DeviceSamples(object):
         self.gamma = None    # [N, K] Student-t gamma of the last E-pass (device)
         self.epass = None    # (K, live, mode, record fingerprint, local sums[2]) of an E-pass computed ahead (PMC.run)
 
+    def weigh(self, proposal, log_target):
+        """Importance weights w_n = exp(log_target_n - log q(x_n)) of these samples under ``proposal`` (extension).
+
+        An importance-sampling step evaluates the proposal at every sample for the weights
+        (importance_sampling.py:203-207) and the PMC update that follows evaluates it again, at the same samples,
+        for the responsibilities (pmc.pyx:23-43).  Here ONE launch of K1 yields log q and rho; the weights are formed
+        from it, stored as this object's weights, and the next ``gaussian_pmc`` / ``student_t_pmc`` call on
+        ``(self, proposal)`` re-uses the responsibilities instead of launching K1 again.
+
+        :param proposal: the :class:`MixtureDensity` the samples were drawn from (unchanged until the update).
+        :param log_target: N log-values of the target at the samples (CUDA tensor or ndarray).
+        :return: the weights as a CUDA tensor (also kept in ``self.w``).
+        """
+        t = _dev.torch()
+        mode = proposal._require_mode()
+        K, N = len(proposal), self.N
+        live = _live_components(proposal)
+        student = (mode == _lib.MODE_STUDENT_T)
+        _alloc_e_buffers(self, N, K, len(live), student)
+        packed = proposal._packed(live)
+        logq = t.empty(N, dtype=t.float64, device=self.x.device)
+        run_k1(self.x, packed, K, mode, logq=logq, resp=self.rho, aux=self.gamma if student else None)
+        lt = log_target if _dev.is_device_tensor(log_target) else _dev.to_device(_np.asarray(log_target, dtype=_np.float64))
+        self.w = t.exp(lt - logq)
+        sums = t.stack([(self.w * logq).sum(), self.w.sum()])       # what K1 would have left in the packet
+        self.epass = (K, tuple(live), mode, _fingerprint(packed), sums)
+        return self.w
+
 
 def _check_arguments(samples, weights, latent, mincount, rb):
     """Argument contradictions, same messages as pmc.pyx:70-83."""

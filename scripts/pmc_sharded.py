@@ -57,6 +57,8 @@ def main():
     ap.add_argument("--D", type=int, default=30)
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--fused", action="store_true",
+                    help="weights and responsibilities from ONE proposal evaluation (DeviceSamples.weigh)")
     args = ap.parse_args()
 
     from pypmc_b200 import parallel
@@ -85,11 +87,17 @@ def main():
         e[0].record()
         x = prop.propose_device(n, rng, seed=777, index0=rank * n)   # K3 (multinomial counts on the host)
         e[1].record()
-        logq = prop.multi_evaluate(x)                       # K1 (proposal)
         logp = target.multi_evaluate(x)                     # K1 (target)
-        wts = torch.exp(logp - logq)                        # importance weights
-        e[2].record()
-        new = gaussian_pmc(DeviceSamples(x, wts), prop)     # K1 (rho) + K2 + all-reduce + host update
+        if args.fused:
+            ds = DeviceSamples(x)
+            ds.weigh(prop, logp)                            # K1 (proposal): log q -> weights, and rho for the update
+            e[2].record()
+            new = gaussian_pmc(ds, prop)                    # K2 + all-reduce + host update (rho re-used)
+        else:
+            logq = prop.multi_evaluate(x)                   # K1 (proposal)
+            wts = torch.exp(logp - logq)                    # importance weights
+            e[2].record()
+            new = gaussian_pmc(DeviceSamples(x, wts), prop)     # K1 (rho) + K2 + all-reduce + host update
         torch.cuda.synchronize()
         tsplit.update(propose_ms=e[0].elapsed_time(e[1]), weight_ms=e[1].elapsed_time(e[2]), x=x)
         return new
@@ -142,7 +150,7 @@ def main():
     if rank == 0:
         print(json.dumps({"workload": "PMC iteration: propose + 2x multi_evaluate + gaussian_pmc, N=%d/GPU K=%d D=%d" % (n, K, D),
                           "n_gpus": world, "s_per_iteration": float(t[0]), "pairs_per_s": world * n * K / float(t[0]),
-                          "propose_ms": tsplit["propose_ms"], "weight_ms": tsplit["weight_ms"],
+                          "fused": bool(args.fused), "propose_ms": tsplit["propose_ms"], "weight_ms": tsplit["weight_ms"],
                           "ranks_identical": bool(ok.item()), "max_rel_diff_vs_unsharded": check,
                           "times": times}))
     if world > 1:

@@ -631,3 +631,48 @@ np.savez(sys.argv[1], **res)
     for key in outs["mma"]:
         a, b = outs["mma"][key], outs["dfma"][key]
         assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-9)) < 1e-11, key
+
+
+def test_weigh_reuses_the_e_pass(pm):
+    """DeviceSamples.weigh: one K1 launch gives the importance weights AND the responsibilities of the update that
+    follows; the result must be the update of the two-launch flow, bit for bit, and a different mixture must not
+    pick the cached pass up."""
+    import torch
+    from pypmc_b200 import _lib
+    from pypmc_b200.density.mixture import create_gaussian_mixture, create_t_mixture
+    from pypmc_b200.mix_adapt.pmc import gaussian_pmc, student_t_pmc, DeviceSamples
+    K, D, N = 6, 9, 20011
+    means, covs, w, _, _ = _synth(K, D, 10, seed=41)
+    tmeans = means + 0.1
+    for student in (False, True):
+        if student:
+            prop = create_t_mixture(means, covs, np.linspace(3, 9, K), w)
+            target = create_t_mixture(tmeans, covs, np.linspace(3, 9, K), w)
+            update = student_t_pmc
+        else:
+            prop = create_gaussian_mixture(means, covs, w)
+            target = create_gaussian_mixture(tmeans, covs, w)
+            update = gaussian_pmc
+        x = prop.propose_device(N, np.random.RandomState(4), seed=11)
+        logp = target.multi_evaluate(x)
+        # two-launch flow
+        wts = torch.exp(logp - prop.multi_evaluate(x))
+        ref = update(DeviceSamples(x, wts), prop)
+        # fused flow
+        ds = DeviceSamples(x)
+        launches0 = _lib.Context.get().launch_count()
+        wf = ds.weigh(prop, logp)
+        new = update(ds, prop)
+        used = _lib.Context.get().launch_count() - launches0
+        assert torch.equal(wf, wts)
+        np.testing.assert_array_equal(new.weights, ref.weights)
+        for a, b in zip(new.components, ref.components):
+            np.testing.assert_array_equal(a.mu, b.mu)
+            np.testing.assert_array_equal(a.sigma, b.sigma)
+        assert used <= 10                                   # one K1 (prepare, fast, exact, finish) + K2 launches, no second K1
+        # stale pass + different mixture: recomputed, not reused
+        ds2 = DeviceSamples(x)
+        ds2.weigh(prop, logp)
+        other = update(ds2, target)
+        ref2 = update(DeviceSamples(x, wts), target)
+        np.testing.assert_array_equal(other.weights, ref2.weights)
