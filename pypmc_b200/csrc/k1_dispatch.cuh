@@ -3,7 +3,7 @@
 // (k1_mixture_eval.cuh) on the same stream; the device-side flag written by k1_prepare decides which of the
 // two does the work (the other returns immediately).
 #pragma once
-#include "k1_fast_eval.cuh"
+#include "k1_mma_eval.cuh"
 
 namespace pmc {
 
@@ -13,7 +13,15 @@ struct K1Launch {
   const double* shift;      // [DP]
   const int* flag;
   double* rowstat;          // [n, 2] for k1_finish, or null
+  // matrix-instruction form (k1_mma_eval.cuh); mma_cb == 0: not offered for this launch
+  const double* theta = nullptr;
+  int mma_cb = 0, mma_nb = 0, mma_steps = 0, mma_kp = 0, mma_ys = 0;
 };
+
+// k1_mma_eval<CB, NB> instantiations (k1_mma.cu): picks (CB, NB) for kl components of dimension d, 0 if the form does
+// not apply (too few components, theta + sample slices beyond the shared memory of an SM)
+bool k1_mma_config(int kl, int d, int* cb, int* nb);
+int k1_mma_launch(const K1Launch& l, int sm_count, cudaStream_t stream);
 
 // returns cudaError_t as int; grid <= #SMs (persistent CTAs, one per SM)
 template <int DP>

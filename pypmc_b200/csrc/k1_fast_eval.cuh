@@ -40,7 +40,7 @@ constexpr double kFastMaxBias = 1.0e4;   // above this |b| the exact-difference 
 struct FastArgs {
   EvalArgs e;             // e.records = derived records (centre slot holds -b_k)
   const double* shift;    // [DP] c
-  const int* flag;        // 0: fast form runs; 1: exact-difference form runs
+  const int* flag;        // flag[0] != 0: exact-difference form runs; else flag[1] != 0: k1_mma_eval runs; else this one
   double* rowstat;        // [n, 2] per-row (running max, 1/denominator) for k1_finish, or null when no second pass follows
 };
 
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(FastCfg<DP>::NW * 32, 1) k1_fast_eval(const Fa
   constexpr int NT = tri_len(DP);
   constexpr uint32_t REC_BYTES = RL * sizeof(double);
   const EvalArgs& a = fa.e;
-  if (*fa.flag != 0) return;                                            // exact-difference kernel takes over
+  if (fa.flag[0] != 0 || fa.flag[1] != 0) return;                      // another form takes over
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* ring = reinterpret_cast<double*>(smem_raw);                  // [NS][RL]

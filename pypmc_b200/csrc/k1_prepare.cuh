@@ -1,20 +1,23 @@
 // k1_prepare.cuh -- the one-CTA prologue of every K1 launch (included by pmcb200.cu only).
 #pragma once
-#include "k1_fast_eval.cuh"
+#include "k1_mma_eval.cuh"
 
 namespace pmc {
 
 // ---------------------------------------------------------------------------------------------
 // k1_prepare: one CTA.  c = sum_k w_k mu_k / sum_k w_k (plain mean if the weights are unusable),
-// derived record k = [T_k | -T_k (mu_k - c) | scalars], flag = (max |b| > kFastMaxBias or non-finite).
+// derived record k = [T_k | -T_k (mu_k - c) | scalars], flag[0] = (max |b| > kFastMaxBias or non-finite): the
+// exact-difference form runs; flag[1] = (want_mma and max_k |b_k|^2 <= kMmaMaxBias2): the matrix-instruction form
+// runs (k1_mma_eval.cuh); neither: k1_fast_eval.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 1) k1_prepare(const double* __restrict__ records, int kl, int dp,
                                                      double* __restrict__ derived, double* __restrict__ shift,
-                                                     int* __restrict__ flag, double* __restrict__ partials, int n_partials) {
+                                                     int* __restrict__ flag, double* __restrict__ partials, int n_partials,
+                                                     int want_mma) {
   const int nt = tri_len(dp), rl = record_len(dp);
   __shared__ double c_s[PMC_MAX_DP];
-  __shared__ int bad;
-  if (threadIdx.x == 0) bad = 0;
+  __shared__ int bad, mma_bad;
+  if (threadIdx.x == 0) { bad = 0; mma_bad = 0; }
   for (int i = threadIdx.x; i < n_partials; i += blockDim.x) partials[i] = 0.0;
   for (int j = threadIdx.x; j < dp; j += blockDim.x) {
     double sw = 0.0, sm = 0.0, su = 0.0;
@@ -47,9 +50,69 @@ __global__ void __launch_bounds__(256, 1) k1_prepare(const double* __restrict__ 
     derived[e] = v;
   }
   __syncthreads();
-  if (threadIdx.x == 0) *flag = bad;
+  for (int k = threadIdx.x; k < kl; k += blockDim.x) {
+    double s = 0.0;
+    for (int i = 0; i < dp; ++i) {
+      const double b = derived[size_t(k) * rl + nt + i];
+      s = fma(b, b, s);
+    }
+    if (!(s <= kMmaMaxBias2)) mma_bad = 1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    flag[0] = bad;
+    flag[1] = (want_mma && !bad && !mma_bad) ? 1 : 0;
+  }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// k1_mma_prepare: one CTA per (padded) component: theta_k from the derived record [T | -b | scalars].
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k1_mma_prepare(const double* __restrict__ derived, int kl, int KP, int d, int dp,
+                                                      int steps, double* __restrict__ theta, const int* __restrict__ flag) {
+  if (flag[0] != 0 || flag[1] == 0) return;
+  const int k = blockIdx.x, tid = threadIdx.x;
+  const int nt = tri_len(dp), rl = record_len(dp), F = k1m_features(d);
+  if (k >= kl) {                                                        // padding components: theta = 0
+    for (int f = tid; f < steps * 4; f += blockDim.x) theta[(size_t(f >> 2) * KP + k) * 4 + (f & 3)] = 0.0;
+    return;
+  }
+  __shared__ double Ts[PMC_MAX_DP * PMC_MAX_DP];                        // dense T, row stride dp
+  __shared__ double bs[PMC_MAX_DP], gs[PMC_MAX_DP];
+  __shared__ double b2;
+  const double* rec = derived + size_t(k) * rl;
+  for (int e = tid; e < dp * dp; e += blockDim.x) {
+    const int i = e / dp, j = e - i * dp;
+    Ts[e] = (j <= i) ? rec[2 * (i >> 1) * ((i >> 1) + 1) + 4 * (j >> 1) + 2 * (i & 1) + (j & 1)] : 0.0;
+  }
+  for (int i = tid; i < dp; i += blockDim.x) bs[i] = -rec[nt + i];
+  __syncthreads();
+  for (int i = tid; i < d; i += blockDim.x) {                           // g = T^T b
+    double g = 0.0;
+    for (int r = i; r < d; ++r) g = fma(Ts[r * dp + i], bs[r], g);
+    gs[i] = g;
+  }
+  if (tid == 0) {
+    double s = 0.0;
+    for (int i = 0; i < d; ++i) s = fma(bs[i], bs[i], s);
+    b2 = s;
+  }
+  __syncthreads();
+  for (int f = tid; f < steps * 4; f += blockDim.x) {
+    double v = 0.0;
+    if (f == 0) v = b2;
+    else if (f <= d) v = -2.0 * gs[f - 1];
+    else if (f < F) {
+      int r, c;
+      tri_index(f - 1 - d, r, c);
+      double m = 0.0;
+      for (int u = r; u < d; ++u) m = fma(Ts[u * dp + r], Ts[u * dp + c], m);     // (T^T T)_rc, c <= r
+      v = (r == c) ? m : 2.0 * m;
+    }
+    theta[(size_t(f >> 2) * KP + k) * 4 + (f & 3)] = v;
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // k1_finish: second pass of K1 as a streaming kernel (runs iff the fast form did, *flag == 0).

@@ -263,12 +263,26 @@ static int eval_prepare(pmcb200_ctx* c, DevBuf& prep, const EvalArgs& a, cudaStr
   const size_t n_part = size_t(c->sm_count) * PMC_MAX_WARPS * 2;
   const size_t off_shift = size_t(a.kl) * rl, off_part = off_shift + PMC_MAX_DP, off_flag = off_part + n_part;
   const size_t off_fin = off_flag + 2, n_fin = size_t(c->sm_count) * 8;
-  if (int rc = ensure(prep, (off_fin + n_fin) * sizeof(double))) return rc;
+  // matrix-instruction form: offered unless PMCB200_K1_FORM=dfma (comparison runs), k1_prepare has the last word
+  int cb = 0, nb = 0;
+  const char* form_env = getenv("PMCB200_K1_FORM");
+  const bool want_mma = !(form_env && std::string(form_env) == "dfma") && k1_mma_config(a.kl, a.d, &cb, &nb);
+  const int steps = (k1m_features(a.d) + 3) / 4, kp = 8 * cb;
+  const size_t off_theta = off_fin + n_fin, n_theta = want_mma ? size_t(steps) * kp * 4 : 0;
+  if (int rc = ensure(prep, (off_theta + n_theta) * sizeof(double))) return rc;
   double* base = static_cast<double*>(prep.p);
   k1_prepare<<<1, 256, 0, st>>>(a.records, a.kl, dp, base, base + off_shift, reinterpret_cast<int*>(base + off_flag),
-                                base + off_part, int(n_part));
+                                base + off_part, int(n_part), want_mma ? 1 : 0);
   PMC_CUDA_CHECK(cudaGetLastError());
   c->launches++;
+  if (want_mma) {
+    k1_mma_prepare<<<kp, 256, 0, st>>>(base, a.kl, kp, a.d, dp, steps, base + off_theta,
+                                       reinterpret_cast<const int*>(base + off_flag));
+    PMC_CUDA_CHECK(cudaGetLastError());
+    c->launches++;
+    out->theta = base + off_theta;
+    out->mma_cb = cb; out->mma_nb = nb; out->mma_steps = steps; out->mma_kp = kp; out->mma_ys = k1m_row_stride(a.d);
+  }
   out->derived = base;
   out->shift = base + off_shift;
   out->flag = reinterpret_cast<int*>(base + off_flag);
@@ -295,6 +309,14 @@ static int eval_launch(pmcb200_ctx* c, const K1Launch& prep, DevBuf& rowbuf, con
   const int ts = k1_tile_rows(dp);
   const int64_t tiles = (a0.n + ts - 1) / ts;
   const int grid = int(std::min<int64_t>(tiles, c->sm_count));
+  if (l.mma_cb > 0) {
+    const int em = k1_mma_launch(l, c->sm_count, st);
+    if (em != 0) {
+      set_last_error(std::string("k1 mma launch: ") + cudaGetErrorString(cudaError_t(em)));
+      return 1;
+    }
+    c->launches++;
+  }
   const int e = k1_launch(dp, l, grid, st);
   if (e != 0) {
     set_last_error(std::string("k1 launch: ") + cudaGetErrorString(cudaError_t(e)));

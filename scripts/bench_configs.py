@@ -64,6 +64,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--cases", default=",".join(CASES))
+    ap.add_argument("--kernels", default="k1,k2")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     ctx = _lib.Context.get(0)
@@ -91,7 +92,7 @@ def main():
                 "tflops": flops / med * 1e-9, "frac_fp64_peak": flops / med * 1e-6 / peak,
                 "alg_GBs": nbytes / med * 1e-6, "pairs_per_s": float(N) * K / med * 1e3}
         print(json.dumps(line), flush=True)
-        if "resp" in outs:
+        if "resp" in outs and "k2" in args.kernels:
             F = 1 + D + D * (D + 1) // 2
             out = torch.zeros(K * (F + 2), dtype=torch.float64, device=dev)
             shift = torch.zeros(D, dtype=torch.float64, device=dev)

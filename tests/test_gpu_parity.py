@@ -676,3 +676,58 @@ def test_weigh_reuses_the_e_pass(pm):
         other = update(ds2, target)
         ref2 = update(DeviceSamples(x, wts), target)
         np.testing.assert_array_equal(other.weights, ref2.weights)
+
+
+@pytest.mark.parametrize("K,D,N,dof", [(32, 30, 5003, None), (64, 20, 3001, None), (16, 40, 2000, 4.0), (12, 9, 1537, None),
+                                       (70, 11, 999, 5.0), (33, 13, 700, None), (9, 8, 257, 3.0)])
+def test_k1_matrix_instruction_form(pm, orc, K, D, N, dof):
+    """The DMMA form of K1 (k1_mma_eval.cuh, the default for K >= 9, D >= 8) against the oracle, and against the
+    DFMA form (PMCB200_K1_FORM=dfma, read per call) to rounding: log-pdfs, log q, rho / gamma, a component subset
+    (non-contiguous output columns) and weighted sums."""
+    import torch
+    from pypmc_b200.density.mixture import create_gaussian_mixture, create_t_mixture
+    from pypmc_b200.density._eval import run_k1
+    from pypmc_b200 import _lib
+    means, covs, w, x, sw = _synth(K, D, N, seed=300 + K + D, dof=dof)
+    dofs = None if dof is None else np.linspace(2.5, 9.0, K)
+    comps = orc.Components(means, covs, dofs)
+    lq_ref, ind_ref = orc.mixture_multi_evaluate(x, comps, w)
+    mix = create_gaussian_mixture(means, covs, w) if dofs is None else create_t_mixture(means, covs, dofs, w)
+    mode = _lib.MODE_GAUSS if dofs is None else _lib.MODE_STUDENT_T
+    res = {}
+    old = os.environ.get("PMCB200_K1_FORM")
+    try:
+        for form in ("mma", "dfma"):
+            os.environ["PMCB200_K1_FORM"] = form
+            ind = np.empty((N, K))
+            lq = mix.multi_evaluate(x, individual=ind)
+            assert rel_err(ind, ind_ref) < TOL, form
+            assert rel_err(lq, lq_ref) < TOL, form
+            sub = [1, 4, K - 1]
+            ind2 = np.full((N, K), -7.0)
+            mix.multi_evaluate(x, individual=ind2, components=sub)
+            np.testing.assert_allclose(ind2[:, sub], ind_ref[:, sub], rtol=TOL, atol=0)
+            assert (np.delete(ind2, sub, axis=1) == -7.0).all()
+            xd = torch.from_numpy(x).cuda()
+            rho = torch.zeros((N, K), dtype=torch.float64, device="cuda")
+            aux = torch.zeros((N, K), dtype=torch.float64, device="cuda") if dofs is not None else None
+            lqd = torch.empty(N, dtype=torch.float64, device="cuda")
+            sums = torch.zeros(2, dtype=torch.float64, device="cuda")
+            run_k1(xd, mix._packed(list(range(K))), K, mode, logq=lqd, resp=rho, aux=aux,
+                   weights=torch.from_numpy(sw).cuda(), sums=sums)
+            rho_ref, _ = orc.calculate_rho_rb(x, comps, w, list(range(K)))
+            assert rel_err(rho.cpu().numpy(), rho_ref) < 1e-9, form
+            if dofs is not None:
+                assert rel_err(aux.cpu().numpy(), orc.student_t_gamma(x, comps, list(range(K)))) < TOL, form
+            np.testing.assert_array_equal(lqd.cpu().numpy(), lq)
+            s = sums.cpu().numpy()
+            assert s[1] == pytest.approx(sw.sum(), rel=1e-13) and s[0] == pytest.approx((sw * lq_ref).sum(), rel=1e-11)
+            res[form] = (lq, ind)
+    finally:
+        if old is None:
+            os.environ.pop("PMCB200_K1_FORM", None)
+        else:
+            os.environ["PMCB200_K1_FORM"] = old
+    np.testing.assert_allclose(res["mma"][0], res["dfma"][0], rtol=1e-12, atol=0)
+    np.testing.assert_allclose(res["mma"][1], res["dfma"][1], rtol=1e-12, atol=0)
+    assert not np.array_equal(res["mma"][1], res["dfma"][1])     # two different kernels did run
