@@ -2,45 +2,61 @@
 #include "k1_dispatch.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace pmc {
 
 constexpr size_t kSmemLimit = 227 * 1024;
 
-bool k1_mma_config(int kl, int d, int* cb, int* nb) {
-  if (kl < 9 || kl > 128 || d < 8) return false;      // few components / tiny D: the DFMA form's epilogue-bound regime
-  const int c = (kl <= 16) ? 2 : (kl <= 32) ? 4 : (kl <= 64) ? 8 : 16;
-  const int n = (c == 16) ? 2 : 4;
-  if (k1m_smem_bytes(d, 8 * c, n) > kSmemLimit) return false;
+// (CB, NB, NW) variants compiled in.  16 warps (four per scheduler) measured best: a warp issues at most one DMMA
+// per ~32 clk, the pipe takes one per 16, and a warp in its epilogue issues none (C2: 8 warps 11.3 ms, 12 warps
+// 10.7 ms, 16 warps 10.5 ms; C3: (8,4,8) 12.3 ms, (8,2,12) 11.5 ms, (8,1,16) 11.2 ms).
+static bool have_variant(int cb, int nb, int nw) {
+  return (cb == 2 && nb == 2 && nw == 16) || (cb == 4 && nb == 2 && nw == 16) || (cb == 8 && nb == 1 && nw == 16) ||
+         (cb == 4 && nb == 4 && nw == 8) || (cb == 8 && nb == 2 && nw == 12);
+}
+
+bool k1_mma_config(int kl, int d, int* cb, int* nb, int* nw) {
+  if (kl < 9 || kl > 64 || d < 8) return false;       // few components / tiny D: the DFMA form's epilogue-bound regime
+  const int c = (kl <= 16) ? 2 : (kl <= 32) ? 4 : 8;
+  int n = (c == 8) ? 1 : 2, w = 16;
+  if (const char* env = getenv("PMCB200_K1_MMA_CFG")) {      // "NB,NW": tuning runs
+    int en = 0, ew = 0;
+    if (sscanf(env, "%d,%d", &en, &ew) == 2 && have_variant(c, en, ew)) { n = en; w = ew; }
+  }
+  if (k1m_smem_bytes(d, 8 * c, n, w) > kSmemLimit) return false;
   *cb = c;
   *nb = n;
+  *nw = w;
   return true;
 }
 
-template <int CB, int NB>
+template <int CB, int NB, int NW, bool SECOND>
 static int launch(const MmaArgs& ma, int sm_count, size_t smem, cudaStream_t stream) {
   static PerDeviceFlag attr_flag;
   bool& attr_set = attr_flag.here();
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k1_mma_eval<CB, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemLimit));
+    cudaError_t e = cudaFuncSetAttribute(k1_mma_eval<CB, NB, NW, SECOND>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemLimit));
     if (e != cudaSuccess) return int(e);
     attr_set = true;
   }
-  const int ts = 8 * NB * K1M_NW;
+  const int ts = 8 * NB * NW;
   const int64_t tiles = (ma.e.n + ts - 1) / ts;
   const int grid = int(std::min<int64_t>(tiles, sm_count));
-  k1_mma_eval<CB, NB><<<grid, K1M_NW * 32, smem, stream>>>(ma);
+  k1_mma_eval<CB, NB, NW, SECOND><<<grid, NW * 32, smem, stream>>>(ma);
   return int(cudaGetLastError());
 }
 
 int k1_mma_launch(const K1Launch& l, int sm_count, cudaStream_t stream) {
-  MmaArgs ma{l.base, l.theta, l.shift, l.flag, l.rowstat, l.mma_steps, l.mma_kp, l.mma_ys};
+  MmaArgs ma{l.base, l.theta, l.shift, l.flag, l.mma_steps, l.mma_kp, l.mma_ys};
   ma.e.records = l.derived;
-  const size_t smem = k1m_smem_bytes(l.base.d, l.mma_kp, l.mma_nb);
-  if (l.mma_cb == 2 && l.mma_nb == 4) return launch<2, 4>(ma, sm_count, smem, stream);
-  if (l.mma_cb == 4 && l.mma_nb == 4) return launch<4, 4>(ma, sm_count, smem, stream);
-  if (l.mma_cb == 8 && l.mma_nb == 4) return launch<8, 4>(ma, sm_count, smem, stream);
-  if (l.mma_cb == 16 && l.mma_nb == 2) return launch<16, 2>(ma, sm_count, smem, stream);
+  const size_t smem = k1m_smem_bytes(l.base.d, l.mma_kp, l.mma_nb, l.mma_nw);
+  const bool second = (l.base.resp_out != nullptr) || (l.base.mode == MODE_VB && l.base.lp_out != nullptr);
+#define PMC_K1M_CASE(CBV, NBV, NWV) \
+  if (l.mma_cb == CBV && l.mma_nb == NBV && l.mma_nw == NWV)                                  \
+    return second ? launch<CBV, NBV, NWV, true>(ma, sm_count, smem, stream) : launch<CBV, NBV, NWV, false>(ma, sm_count, smem, stream);
+  PMC_K1M_CASE(2, 2, 16) PMC_K1M_CASE(4, 2, 16) PMC_K1M_CASE(8, 1, 16) PMC_K1M_CASE(4, 4, 8) PMC_K1M_CASE(8, 2, 12)
+#undef PMC_K1M_CASE
   return int(cudaErrorInvalidValue);
 }
 

@@ -21,8 +21,9 @@
 // A warp owns 8 NB samples per tile: it stages x - c (plus the constant column 1 and a zero column) in its private
 // shared-memory slice, then per feature quad loads CB theta fragments, forms NB phi fragments (2 LDS + DMUL each) and
 // issues NB x CB DMMAs into 8x8 (sample x component) accumulators.  A sample's K log-pdfs end up inside one quad of
-// lanes, so the log-sum-exp is two shuffles deep and the N x K output leaves as 16-byte stores, two full sectors per
-// quad.  The second pass (rho / r) is k1_finish, as for the fast form.
+// lanes, so the log-sum-exp is two shuffles deep and the N x K outputs leave as 16-byte stores, two full sectors per
+// quad.  The second pass (rho = exp(lp) w_k / (exp(log q) + tiny), or the VB soft-max with its sum r log r) happens
+// here too, on the log-pdfs still in registers -- k1_finish, the streaming pass behind the DFMA forms, returns at once.
 #pragma once
 
 #include "k1_fast_eval.cuh"
@@ -30,7 +31,6 @@
 namespace pmc {
 
 constexpr double kMmaMaxBias2 = 2.0e4;   // above this |b_k|^2 the DFMA forms run instead
-constexpr int K1M_NW = 8;                // warps per CTA (two per SM sub-partition)
 constexpr int K1M_SCAL = 8;              // scalars per component kept in shared memory
 
 struct MmaArgs {
@@ -38,7 +38,6 @@ struct MmaArgs {
   const double* theta;    // [steps][KP][4]
   const double* shift;    // [d]
   const int* flag;        // flag[0] != 0: exact-difference form runs; else flag[1] != 0: this form runs; else k1_fast_eval
-  double* rowstat;        // [n, 2] per-row (max, 1/denominator) for k1_finish, or null
   int steps;              // feature quads = ceil(F / 4)
   int KP;                 // components padded to 8 CB
   int YS;                 // row stride (doubles) of the staged samples: >= d + 2 and == 4 (mod 16)
@@ -46,9 +45,9 @@ struct MmaArgs {
 
 __host__ __device__ inline int k1m_features(int d) { return 1 + d + d * (d + 1) / 2; }
 __host__ __device__ inline int k1m_row_stride(int d) { return ((d + 2 - 4 + 15) / 16) * 16 + 4; }
-inline size_t k1m_smem_bytes(int d, int KP, int NB) {
+inline size_t k1m_smem_bytes(int d, int KP, int NB, int NW) {
   const int steps = (k1m_features(d) + 3) / 4, YS = k1m_row_stride(d);
-  return sizeof(double) * (size_t(steps) * KP * 4 + size_t(KP) * K1M_SCAL + YS + size_t(K1M_NW) * 8 * NB * YS) +
+  return sizeof(double) * (size_t(steps) * KP * 4 + size_t(KP) * K1M_SCAL + YS + size_t(NW) * 8 * NB * YS) +
          sizeof(int) * size_t(steps) * 4 + 16;
 }
 
@@ -61,13 +60,14 @@ __device__ __forceinline__ void tri_index(int t, int& r, int& c) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// k1_mma_eval<CB, NB>: CB blocks of 8 components (KP = 8 CB), NB blocks of 8 samples per warp and tile.
+// k1_mma_eval<CB, NB, NW, SECOND>: CB blocks of 8 components (KP = 8 CB), NB blocks of 8 samples per warp and tile,
+// NW warps per CTA; SECOND: the launch also wants rho / r (the eval-only instantiation keeps no exponentials).
 // ---------------------------------------------------------------------------------------------
-template <int CB, int NB>
-__global__ void __launch_bounds__(K1M_NW * 32, 1) k1_mma_eval(const MmaArgs ma) {
+template <int CB, int NB, int NW, bool SECOND>
+__global__ void __launch_bounds__(NW * 32, 1) k1_mma_eval(const MmaArgs ma) {
   const EvalArgs& a = ma.e;
   if (ma.flag[0] != 0 || ma.flag[1] == 0) return;
-  constexpr int RW = 8 * NB, TS = RW * K1M_NW, KP = 8 * CB;
+  constexpr int RW = 8 * NB, TS = RW * NW, KP = 8 * CB;
   const int D = a.d, YS = ma.YS, steps = ma.steps;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(K1M_NW * 32, 1) k1_mma_eval(const MmaArgs ma) 
   double* scal_s = theta_s + size_t(steps) * KP * 4;                   // [KP][8]
   double* cs = scal_s + KP * K1M_SCAL;                                 // [YS] shift
   double* y_all = cs + YS;                                             // [NW][RW][YS]
-  int* tab = reinterpret_cast<int*>(y_all + size_t(K1M_NW) * RW * YS); // [steps * 4] (off_i | off_j << 8)
+  int* tab = reinterpret_cast<int*>(y_all + size_t(NW) * RW * YS); // [steps * 4] (off_i | off_j << 8)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, tq = lane & 3;
@@ -100,17 +100,17 @@ __global__ void __launch_bounds__(K1M_NW * 32, 1) k1_mma_eval(const MmaArgs ma) 
       else if (f < F) tri_index(f - 1 - D, oi, oj);
       tab[f] = oi | (oj << 8);
     }
-    for (int i = tid; i < K1M_NW * RW * YS; i += blockDim.x) y_all[i] = ((i % YS) == D) ? 1.0 : 0.0;
+    for (int i = tid; i < NW * RW * YS; i += blockDim.x) y_all[i] = ((i % YS) == D) ? 1.0 : 0.0;
   }
   // contiguous output columns (the usual case) allow 16-byte stores
-  double* const scratch = a.lp_out ? a.lp_out : a.resp_out;
-  const bool staged = scratch != nullptr || a.aux_out != nullptr;
+  const bool staged = a.lp_out != nullptr || a.resp_out != nullptr || a.aux_out != nullptr;
   int contig_l = 1;
   if (staged) {
     const int c0 = __ldg(a.cols);
     for (int k = tid; k < a.kl; k += blockDim.x) contig_l &= (__ldg(a.cols + k) == c0 + k);
     contig_l &= ((c0 & 1) == 0) && ((a.k_out & 1) == 0) && ((a.kl & 1) == 0);
-    contig_l &= (scratch == nullptr) || ((reinterpret_cast<uintptr_t>(scratch) & 15) == 0);
+    contig_l &= (a.lp_out == nullptr) || ((reinterpret_cast<uintptr_t>(a.lp_out) & 15) == 0);
+    contig_l &= (a.resp_out == nullptr) || ((reinterpret_cast<uintptr_t>(a.resp_out) & 15) == 0);
     contig_l &= (a.aux_out == nullptr) || ((reinterpret_cast<uintptr_t>(a.aux_out) & 15) == 0);
   }
   const bool contig = __syncthreads_and(contig_l) != 0;               // also publishes the prologue's stores
@@ -145,8 +145,8 @@ __global__ void __launch_bounds__(K1M_NW * 32, 1) k1_mma_eval(const MmaArgs ma) 
   // The two warps of a scheduler would run in lock step: both in the DMMA loop (sharing the pipe), then both in the
   // latency-bound epilogue (pipe idle, 18 % of the time in the first profile).  Starting the second warp one
   // DMMA-loop later keeps them in opposite phases for the whole kernel: one warp's epilogue hides behind the other's loop.
-  if (warp >= K1M_NW / 2 && num_tiles >= 4 * int64_t(gridDim.x)) {
-    const long long t0 = clock64(), wait = (long long)steps * (NB * CB * 16);
+  if (warp >= 4 && num_tiles >= 4 * int64_t(gridDim.x)) {
+    const long long t0 = clock64(), wait = (long long)steps * (NB * CB * 16) * (warp / 4);
     while (clock64() - t0 < wait) {
     }
   }
@@ -246,8 +246,8 @@ __global__ void __launch_bounds__(K1M_NW * 32, 1) k1_mma_eval(const MmaArgs ma) 
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) mx[nb] = fmax(mx[nb], acc[nb][cb][e]);
       }
-    // log-pdfs leave as 16-byte stores when the output columns are contiguous
-    if (scratch) {
+    // log-pdfs leave as 16-byte stores when the output columns are contiguous (VB: log_rho is written normalised below)
+    auto store_pairs = [&](double* out, const double (&v)[NB][CB][2]) {
 #pragma unroll
       for (int nb = 0; nb < NB; ++nb) {
         const int64_t row = row0 + 8 * nb + g;
@@ -256,23 +256,23 @@ __global__ void __launch_bounds__(K1M_NW * 32, 1) k1_mma_eval(const MmaArgs ma) 
         for (int cb = 0; cb < CB; ++cb) {
           const int k = 8 * cb + 2 * tq;
           if (contig) {
-            if (k < a.kl)
-              *reinterpret_cast<double2*>(scratch + size_t(row) * a.k_out + col0 + k) = make_double2(acc[nb][cb][0], acc[nb][cb][1]);
+            if (k < a.kl) *reinterpret_cast<double2*>(out + size_t(row) * a.k_out + col0 + k) = make_double2(v[nb][cb][0], v[nb][cb][1]);
           } else {
 #pragma unroll
             for (int e = 0; e < 2; ++e)
-              if (k + e < a.kl) scratch[size_t(row) * a.k_out + __ldg(a.cols + k + e)] = acc[nb][cb][e];
+              if (k + e < a.kl) out[size_t(row) * a.k_out + __ldg(a.cols + k + e)] = v[nb][cb][e];
           }
         }
       }
-    }
+    };
+    if (a.lp_out && a.mode != MODE_VB) store_pairs(a.lp_out, acc);
     // weighted log-sum-exp over the components (same value as _regularize.pyx:72-81 up to rounding)
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb) {
       mx[nb] = fmax(mx[nb], __shfl_xor_sync(0xffffffffu, mx[nb], 1));
       mx[nb] = fmax(mx[nb], __shfl_xor_sync(0xffffffffu, mx[nb], 2));
     }
-    double sum[NB];
+    double ex[SECOND ? NB : 1][CB][2], sum[NB];
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb) sum[nb] = 0.0;
 #pragma unroll
@@ -281,28 +281,86 @@ __global__ void __launch_bounds__(K1M_NW * 32, 1) k1_mma_eval(const MmaArgs ma) 
       for (int e = 0; e < 2; ++e) {
         const double wk = scal_s[(8 * cb + 2 * tq + e) * K1M_SCAL + S_WEIGHT];
 #pragma unroll
-        for (int nb = 0; nb < NB; ++nb) sum[nb] = fma(wk, exp(acc[nb][cb][e] - mx[nb]), sum[nb]);
+        for (int nb = 0; nb < NB; ++nb) {
+          const double t = wk * exp(acc[nb][cb][e] - mx[nb]);
+          if constexpr (SECOND) ex[nb][cb][e] = t;
+          sum[nb] += t;
+        }
       }
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb) {
       sum[nb] += __shfl_xor_sync(0xffffffffu, sum[nb], 1);
       sum[nb] += __shfl_xor_sync(0xffffffffu, sum[nb], 2);
     }
-    // ---- per-sample results: lane tq == nb % 4 of the quad finishes sample nb ----
+    // ---- per-sample results: lane tq == nb % 4 of the quad finishes sample nb and hands the quad what the
+    //      second pass needs (the DFMA forms leave that pass to k1_finish; here the log-pdfs are still in registers) ----
+    constexpr bool second = SECOND;     // host: (resp_out != null) || (mode == VB && lp_out != null)
+    double f0[NB], f1[NB];          // mixtures: 1 / (exp(log q) + tiny), exp(max) * that;  VB: 1 / norm, ln(1 / norm)
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb) {
       const int64_t row = row0 + 8 * nb + g;
-      if (row < a.n && tq == (nb & 3)) {
+      f0[nb] = 0.0;
+      f1[nb] = 0.0;
+      if (tq == (nb & 3)) {
         const double lq = log(sum[nb]) + mx[nb];                        // _regularize.pyx:81
-        const double w_n = a.sw ? __ldg(a.sw + row) : 1.0;
-        part_w += w_n;
-        if (a.logq) a.logq[row] = lq;
-        if (a.mode != MODE_VB) part_a += w_n * lq;                      // pmc.pyx:388-391
-        if (ma.rowstat) {
-          ma.rowstat[2 * row] = mx[nb];
-          ma.rowstat[2 * row + 1] = (a.mode != MODE_VB) ? 1.0 / (exp(lq) + kTiny)   // pmc.pyx:39-41
-                                                        : 1.0 / sum[nb];            // variational.pyx:728-755
+        if (row < a.n) {
+          const double w_n = a.sw ? __ldg(a.sw + row) : 1.0;
+          part_w += w_n;
+          if (a.logq) a.logq[row] = lq;
+          if (a.mode != MODE_VB) part_a += w_n * lq;                    // pmc.pyx:388-391
         }
+        if (second) {
+          if (a.mode != MODE_VB) {
+            f0[nb] = 1.0 / (exp(lq) + kTiny);                           // pmc.pyx:39-41
+            f1[nb] = exp(mx[nb]) * f0[nb];
+          } else {
+            f0[nb] = 1.0 / sum[nb];                                     // variational.pyx:728-755
+            f1[nb] = log(f0[nb]);
+          }
+        }
+      }
+      if (second) {
+        f0[nb] = __shfl_sync(0xffffffffu, f0[nb], (lane & ~3) | (nb & 3));
+        f1[nb] = __shfl_sync(0xffffffffu, f1[nb], (lane & ~3) | (nb & 3));
+      }
+    }
+    if constexpr (SECOND) {
+      if (a.mode != MODE_VB) {
+        // rho_nk = exp(lp_nk) w_k / (exp(log q_n) + tiny) = [w_k exp(lp_nk - max)] [exp(max) / (exp(log q_n) + tiny)];
+        // where exp(lp_nk) is subnormal the reference's own rounding is reproduced by its literal formula
+#pragma unroll
+        for (int cb = 0; cb < CB; ++cb)
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) {
+              double r = ex[nb][cb][e] * f1[nb];
+              if (acc[nb][cb][e] < -700.0 || mx[nb] > 700.0)
+                r = exp(acc[nb][cb][e]) * scal_s[(8 * cb + 2 * tq + e) * K1M_SCAL + S_WEIGHT] * f0[nb];
+              ex[nb][cb][e] = r;
+            }
+        store_pairs(a.resp_out, ex);
+      } else {
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+          const int64_t row = row0 + 8 * nb + g;
+          const double w_r = (a.sw && row < a.n) ? __ldg(a.sw + row) : 1.0;
+          double s_rl = 0.0;
+#pragma unroll
+          for (int cb = 0; cb < CB; ++cb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              double rv = ex[nb][cb][e] * f0[nb];
+              if (rv == 0.0) rv = kTiny;                                              // variational.pyx:753-754
+              const double lrn = (acc[nb][cb][e] - mx[nb]) + f1[nb];                  // variational.pyx:741,755
+              ex[nb][cb][e] = rv;
+              acc[nb][cb][e] = lrn;
+              if (8 * cb + 2 * tq + e < a.kl) s_rl = fma(w_r * rv, lrn, s_rl);        // variational.pyx:1003-1013
+            }
+          if (row < a.n) part_a += s_rl;
+        }
+        if (a.resp_out) store_pairs(a.resp_out, ex);
+        if (a.lp_out) store_pairs(a.lp_out, acc);
       }
     }
   }

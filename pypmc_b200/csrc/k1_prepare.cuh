@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256) k1_mma_prepare(const double* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
-// k1_finish: second pass of K1 as a streaming kernel (runs iff the fast form did, *flag == 0).
+// k1_finish: second pass of K1 as a streaming kernel (runs iff the fast form did: flag[0] == 0 and flag[1] == 0).
 //   mixture modes : rho_nk = exp(lp_nk) w_k / (exp(log q_n) + tiny)                 pmc.pyx:39-41
 //   VB mode       : r_nk = exp(lp - max) / norm (zeros -> tiny), log_rho <- lp - max + ln(1/norm),
 //                   partial sums of w_n r_nk log r_nk                               variational.pyx:728-755, 1003-1013
@@ -138,7 +138,7 @@ struct FinishArgs {
 };
 
 __global__ void __launch_bounds__(256, 4) k1_finish(const FinishArgs a) {
-  if (*a.flag != 0) return;
+  if (a.flag[0] != 0 || a.flag[1] != 0) return;      // exact-difference form / matrix-instruction form: pass already done
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int hw = (a.kl > 16) ? 32 : (a.kl > 8) ? 16 : (a.kl > 4) ? 8 : 4;
   const int per = 32 / hw, l_k = lane % hw, l_r = lane / hw;
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(256, 4) k1_finish(const FinishArgs a) {
 // sums[0] += sum_b fin_partials[b] in block order (VB: sum_n w_n sum_k r log r)
 __global__ void k1_reduce_finish(const double* __restrict__ fin_partials, int count, const int* __restrict__ flag,
                                  double* __restrict__ sums) {
-  if (*flag != 0 || threadIdx.x != 0) return;
+  if (flag[0] != 0 || flag[1] != 0 || threadIdx.x != 0) return;
   double s = 0.0;
   for (int i = 0; i < count; ++i) s += fin_partials[i];
   sums[0] += s;

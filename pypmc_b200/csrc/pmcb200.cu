@@ -264,9 +264,9 @@ static int eval_prepare(pmcb200_ctx* c, DevBuf& prep, const EvalArgs& a, cudaStr
   const size_t off_shift = size_t(a.kl) * rl, off_part = off_shift + PMC_MAX_DP, off_flag = off_part + n_part;
   const size_t off_fin = off_flag + 2, n_fin = size_t(c->sm_count) * 8;
   // matrix-instruction form: offered unless PMCB200_K1_FORM=dfma (comparison runs), k1_prepare has the last word
-  int cb = 0, nb = 0;
+  int cb = 0, nb = 0, nw = 0;
   const char* form_env = getenv("PMCB200_K1_FORM");
-  const bool want_mma = !(form_env && std::string(form_env) == "dfma") && k1_mma_config(a.kl, a.d, &cb, &nb);
+  const bool want_mma = !(form_env && std::string(form_env) == "dfma") && k1_mma_config(a.kl, a.d, &cb, &nb, &nw);
   const int steps = (k1m_features(a.d) + 3) / 4, kp = 8 * cb;
   const size_t off_theta = off_fin + n_fin, n_theta = want_mma ? size_t(steps) * kp * 4 : 0;
   if (int rc = ensure(prep, (off_theta + n_theta) * sizeof(double))) return rc;
@@ -281,7 +281,7 @@ static int eval_prepare(pmcb200_ctx* c, DevBuf& prep, const EvalArgs& a, cudaStr
     PMC_CUDA_CHECK(cudaGetLastError());
     c->launches++;
     out->theta = base + off_theta;
-    out->mma_cb = cb; out->mma_nb = nb; out->mma_steps = steps; out->mma_kp = kp; out->mma_ys = k1m_row_stride(a.d);
+    out->mma_cb = cb; out->mma_nb = nb; out->mma_nw = nw; out->mma_steps = steps; out->mma_kp = kp; out->mma_ys = k1m_row_stride(a.d);
   }
   out->derived = base;
   out->shift = base + off_shift;
