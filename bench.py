@@ -281,12 +281,12 @@ def run_gpu(args):
     peaks, peak_src = measured_peaks()
     hbm_bytes = BYTES_PER_SAMPLE * float(n)
     hbm_gbs = hbm_bytes / (kernel_ms * 1e-3) * 1e-9
-    traffic = None
+    traffic, kernel_name = None, "k1_mma_eval<4, 2, 16, false>"
     tpath = os.path.join(ROOT, "profiles", "k1_ncu_traffic.json")   # dram bytes per launch from the committed ncu capture
     if os.path.exists(tpath):
         with open(tpath) as fh:
             tj = json.load(fh)
-        if tj.get("rows") == n:
+        if tj.get("rows") == n and "k1_mma_eval" in tj.get("kernel", ""):
             traffic = tj.get("dram_bytes_per_launch")
     roofline = {
         "bound": "fp64", "achieved": achieved_tf, "peak": peak_gflops * 1e-3, "unit": "TFLOP/s",
@@ -294,7 +294,7 @@ def run_gpu(args):
         "peak_source": "measured: DFMA microbenchmark run in this process (pmcb200_fp64_peak, register-resident "
                        "chains on every SM, burst); MEASURED_PEAKS.json has no FP64 entry",
         "peak_sustained": sustained_gflops * 1e-3, "peak_sustained_ms": sustained_ms,
-        "kernel": "k1_fast_eval<30>", "kernel_ms": kernel_ms, "algorithmic_flops_per_launch": flops,
+        "kernel": kernel_name, "kernel_ms": kernel_ms, "algorithmic_flops_per_launch": flops,
         "hbm": {"achieved": hbm_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_gbs / peaks["hbm_gbs"],
                 "algorithmic_bytes_per_launch": hbm_bytes, "peak_source": peak_src},
     }

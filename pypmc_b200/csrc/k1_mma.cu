@@ -10,7 +10,7 @@ constexpr size_t kSmemLimit = 227 * 1024;
 
 // (CB, NB, NW) variants compiled in.  16 warps (four per scheduler) measured best: a warp issues at most one DMMA
 // per ~32 clk, the pipe takes one per 16, and a warp in its epilogue issues none (C2: 8 warps 11.3 ms, 12 warps
-// 10.7 ms, 16 warps 10.5 ms; C3: (8,4,8) 12.3 ms, (8,2,12) 11.5 ms, (8,1,16) 11.2 ms).
+// 10.7 ms, 16 warps 10.5 ms; C3: (8,4,8) 12.3 ms, (8,2,12) 11.5 ms, (8,2,16) 11.8 ms with spills, (8,1,16) 11.1 ms).
 static bool have_variant(int cb, int nb, int nw) {
   return (cb == 2 && nb == 2 && nw == 16) || (cb == 4 && nb == 2 && nw == 16) || (cb == 8 && nb == 1 && nw == 16) ||
          (cb == 4 && nb == 4 && nw == 8) || (cb == 8 && nb == 2 && nw == 12);

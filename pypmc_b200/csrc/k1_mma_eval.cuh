@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k1_mma_eval(const MmaArgs ma) {
   const EvalArgs& a = ma.e;
   if (ma.flag[0] != 0 || ma.flag[1] == 0) return;
   constexpr int RW = 8 * NB, TS = RW * NW, KP = 8 * CB;
+  constexpr int UNR = (CB * NB <= 4) ? 4 : 2;          // feature quads per loop body (at least 16 DMMAs)
   const int D = a.d, YS = ma.YS, steps = ma.steps;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k1_mma_eval(const MmaArgs ma) {
       for (int nb = 0; nb < NB; ++nb) { yi_n[nb] = yi[nb * 8 * YS]; yj_n[nb] = yj[nb * 8 * YS]; }
     };
     fetch(0);
-#pragma unroll 2
+#pragma unroll UNR
     for (int s = 0; s < steps; ++s) {
       double th[CB], ph[NB];
 #pragma unroll

@@ -4,16 +4,17 @@
 TAG=${1:-r01}
 mkdir -p gpurun_out
 timeout 300 python scripts/bench_configs.py --reps 5 > gpurun_out/configs_$TAG.log 2>&1
+timeout 600 python scripts/bench_updates.py > gpurun_out/updates_$TAG.log 2>&1
 timeout 600 python bench.py > gpurun_out/bench_$TAG.log 2>&1
 timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref_$TAG.log 2>&1
 # (1) every launch of the bench command with its device time
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
     --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 4 --warmup 3 --e2e-rows 1000000 > gpurun_out/bench_under_ncu_$TAG.log 2>&1
 # (2) the dominant kernel of the bench step, full set, at the bench workload (N = 1e7)
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k1_fast_eval -s 3 -c 1 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k1_mma_eval -s 3 -c 1 \
     -o gpurun_out/k1_full_$TAG -f python bench.py --steps 2 --warmup 3 --e2e-rows 1000000 > gpurun_out/k1_full_$TAG.log 2>&1
 # (3) K1 with responsibilities + K2 on the update workload (config 2, N = 1e7)
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k1_fast_eval|k2_suffstats" -s 1 -c 2 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k1_mma_eval|k2_suffstats" -s 1 -c 2 \
     -o gpurun_out/update_full_$TAG -f python scripts/bench_configs.py --reps 1 --cases c2_rho > gpurun_out/update_full_$TAG.log 2>&1
 cat gpurun_out/configs_$TAG.log | cut -c1-330
 grep '^{' gpurun_out/bench_$TAG.log | cut -c1-2500

@@ -139,8 +139,9 @@ def summarize_launches(tag):
     lines = ["# Launch list of `python bench.py --steps 4 --warmup 3 --e2e-rows 1000000` under ncu", "",
              "`ncu --metrics gpu__time_duration.sum --clock-control none` (one pass per kernel, serialised, cold caches:",
              "compare SHARES, not absolutes).  %d launches captured.  The torch kernels are the synthetic-sample" % len(launches),
-             "generation before the timed region; a timed step launches exactly k1_prepare, k1_fast_eval and",
-             "k1_mixture_eval (the exact-difference form, which returns at once unless k1_prepare raised its flag).", "",
+             "generation before the timed region; a timed step launches exactly k1_prepare, k1_mma_prepare, k1_mma_eval",
+             "(the matrix-instruction form, which does the work) and k1_fast_eval / k1_mixture_eval (the DFMA forms, which",
+             "return at once unless k1_prepare's flags hand them the launch).", "",
              "| kernel | launches | total ms | share of the step kernels (k1_*) |", "|---|---|---|---|"]
     for k, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         share = ("%.1f %%" % (100 * ms / tot_ours) if k in ours else
@@ -160,7 +161,7 @@ def main():
     tag = sys.argv[1]
     os.makedirs(PROF, exist_ok=True)
     done = [summarize_launches(tag)]
-    done += summarize_rep(os.path.join(OUT, "k1_full_%s.ncu-rep" % tag), tag + "_bench", traffic_for="k1_fast_eval")
+    done += summarize_rep(os.path.join(OUT, "k1_full_%s.ncu-rep" % tag), tag + "_bench", traffic_for="k1_mma_eval")
     done += summarize_rep(os.path.join(OUT, "update_full_%s.ncu-rep" % tag), tag + "_update")
     for name in ("configs_%s.log" % tag, "bench_%s.log" % tag, "bench_ref_%s.log" % tag):
         src = os.path.join(OUT, name)
