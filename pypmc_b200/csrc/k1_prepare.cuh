@@ -5,37 +5,39 @@
 namespace pmc {
 
 // ---------------------------------------------------------------------------------------------
-// k1_prepare: one CTA.  c = sum_k w_k mu_k / sum_k w_k (plain mean if the weights are unusable),
-// derived record k = [T_k | -T_k (mu_k - c) | scalars], flag[0] = (max |b| > kFastMaxBias or non-finite): the
+// k1_prepare: one CTA per evaluated component (a single CTA took 62 us at K=32, D=30: 0.6 % of a pass at N=1e7 and
+// most of a small one).  Every CTA forms the shift c = sum_k w_k mu_k / sum_k w_k (plain mean if the weights are
+// unusable) in the same fixed order, then its derived record [T_k | -T_k (mu_k - c) | scalars].  The last CTA to
+// finish combines the per-component verdicts: flag[0] = (max |b| > kFastMaxBias or non-finite): the
 // exact-difference form runs; flag[1] = (want_mma and max_k |b_k|^2 <= kMmaMaxBias2): the matrix-instruction form
-// runs (k1_mma_eval.cuh); neither: k1_fast_eval.
+// runs (k1_mma_eval.cuh); neither: k1_fast_eval.  flag[2] (arrival counter) and flag[3] (verdict bits) are zero
+// between launches (cleared at allocation and by the last CTA).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 1) k1_prepare(const double* __restrict__ records, int kl, int dp,
-                                                     double* __restrict__ derived, double* __restrict__ shift,
-                                                     int* __restrict__ flag, double* __restrict__ partials, int n_partials,
-                                                     int want_mma) {
-  const int nt = tri_len(dp), rl = record_len(dp);
-  __shared__ double c_s[PMC_MAX_DP];
-  __shared__ int bad, mma_bad;
-  if (threadIdx.x == 0) { bad = 0; mma_bad = 0; }
-  for (int i = threadIdx.x; i < n_partials; i += blockDim.x) partials[i] = 0.0;
+__global__ void __launch_bounds__(128) k1_prepare(const double* __restrict__ records, int kl, int dp,
+                                                  double* __restrict__ derived, double* __restrict__ shift,
+                                                  int* __restrict__ flag, double* __restrict__ partials, int n_partials,
+                                                  int want_mma) {
+  const int nt = tri_len(dp), rl = record_len(dp), k = blockIdx.x;
+  __shared__ double c_s[PMC_MAX_DP], b_s[PMC_MAX_DP];
+  __shared__ int bad;
+  if (threadIdx.x == 0) bad = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_partials; i += gridDim.x * blockDim.x) partials[i] = 0.0;
   for (int j = threadIdx.x; j < dp; j += blockDim.x) {
     double sw = 0.0, sm = 0.0, su = 0.0;
-    for (int k = 0; k < kl; ++k) {                       // fixed order
-      const double w = records[size_t(k) * rl + nt + dp + S_WEIGHT];
-      const double m = records[size_t(k) * rl + nt + j];
+    for (int kk = 0; kk < kl; ++kk) {                    // fixed order
+      const double w = records[size_t(kk) * rl + nt + dp + S_WEIGHT];
+      const double m = records[size_t(kk) * rl + nt + j];
       sw += w; sm += w * m; su += m;
     }
     double c = sm / sw;
     if (!(sw > 0.0) || !isfinite(c)) c = su / kl;
     if (!isfinite(c)) c = 0.0;
     c_s[j] = c;
-    shift[j] = c;
+    if (k == 0) shift[j] = c;
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < kl * rl; e += blockDim.x) {
-    const int k = e / rl, o = e - k * rl;
-    const double* rec = records + size_t(k) * rl;
+  const double* rec = records + size_t(k) * rl;
+  for (int o = threadIdx.x; o < rl; o += blockDim.x) {
     double v = rec[o];
     if (o >= nt && o < nt + dp) {                        // centre slot -> -b_i,  i = o - nt
       const int i = o - nt, r = i >> 1;
@@ -45,23 +47,25 @@ __global__ void __launch_bounds__(256, 1) k1_prepare(const double* __restrict__ 
         b = fma(t, rec[nt + j] - c_s[j], b);
       }
       if (!(fabs(b) <= kFastMaxBias)) bad = 1;           // also catches NaN
+      b_s[i] = b;
       v = -b;
     }
-    derived[e] = v;
-  }
-  __syncthreads();
-  for (int k = threadIdx.x; k < kl; k += blockDim.x) {
-    double s = 0.0;
-    for (int i = 0; i < dp; ++i) {
-      const double b = derived[size_t(k) * rl + nt + i];
-      s = fma(b, b, s);
-    }
-    if (!(s <= kMmaMaxBias2)) mma_bad = 1;
+    derived[size_t(k) * rl + o] = v;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    flag[0] = bad;
-    flag[1] = (want_mma && !bad && !mma_bad) ? 1 : 0;
+    double s = 0.0;
+    for (int i = 0; i < dp; ++i) s = fma(b_s[i], b_s[i], s);
+    const int bits = (bad ? 1 : 0) | (!(s <= kMmaMaxBias2) ? 2 : 0);
+    if (bits) atomicOr(&flag[3], bits);
+    __threadfence();
+    if (atomicAdd(&flag[2], 1) == int(gridDim.x) - 1) {  // last CTA: every verdict is in
+      __threadfence();
+      const int all = atomicExch(&flag[3], 0);
+      flag[0] = all & 1;
+      flag[1] = (want_mma && all == 0) ? 1 : 0;
+      flag[2] = 0;
+    }
   }
 }
 

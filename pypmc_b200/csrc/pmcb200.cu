@@ -111,6 +111,8 @@ static int ensure(DevBuf& b, size_t bytes) {
   b.p = nullptr;
   b.bytes = 0;
   PMC_CUDA_CHECK(cudaMalloc(&b.p, bytes));
+  PMC_CUDA_CHECK(cudaMemset(b.p, 0, bytes));     // k1_prepare's arrival counter / verdict bits start at zero
+  PMC_CUDA_CHECK(cudaDeviceSynchronize());       // (allocation time only) the caller's stream may be non-blocking
   b.bytes = bytes;
   return 0;
 }
@@ -261,8 +263,10 @@ static int eval_prepare(pmcb200_ctx* c, DevBuf& prep, const EvalArgs& a, cudaStr
   const int dp = (a.d + 1) & ~1;
   const int rl = record_len(dp);
   const size_t n_part = size_t(c->sm_count) * PMC_MAX_WARPS * 2;
-  const size_t off_shift = size_t(a.kl) * rl, off_part = off_shift + PMC_MAX_DP, off_flag = off_part + n_part;
-  const size_t off_fin = off_flag + 2, n_fin = size_t(c->sm_count) * 8;
+  // layout (doubles): [flags (4 ints) | derived records | shift | per-warp partials | finish partials | theta]; the flags
+  // sit at a FIXED place because k1_prepare's counter / verdict bits must read zero whatever was launched before
+  const size_t off_flag = 0, off_rec = 2, off_shift = off_rec + size_t(a.kl) * rl, off_part = off_shift + PMC_MAX_DP;
+  const size_t off_fin = off_part + n_part, n_fin = size_t(c->sm_count) * 8;
   // matrix-instruction form: offered unless PMCB200_K1_FORM=dfma (comparison runs), k1_prepare has the last word
   int cb = 0, nb = 0, nw = 0;
   const char* form_env = getenv("PMCB200_K1_FORM");
@@ -271,19 +275,19 @@ static int eval_prepare(pmcb200_ctx* c, DevBuf& prep, const EvalArgs& a, cudaStr
   const size_t off_theta = off_fin + n_fin, n_theta = want_mma ? size_t(steps) * kp * 4 : 0;
   if (int rc = ensure(prep, (off_theta + n_theta) * sizeof(double))) return rc;
   double* base = static_cast<double*>(prep.p);
-  k1_prepare<<<1, 256, 0, st>>>(a.records, a.kl, dp, base, base + off_shift, reinterpret_cast<int*>(base + off_flag),
+  k1_prepare<<<a.kl, 128, 0, st>>>(a.records, a.kl, dp, base + off_rec, base + off_shift, reinterpret_cast<int*>(base + off_flag),
                                 base + off_part, int(n_part), want_mma ? 1 : 0);
   PMC_CUDA_CHECK(cudaGetLastError());
   c->launches++;
   if (want_mma) {
-    k1_mma_prepare<<<kp, 256, 0, st>>>(base, a.kl, kp, a.d, dp, steps, base + off_theta,
+    k1_mma_prepare<<<kp, 256, 0, st>>>(base + off_rec, a.kl, kp, a.d, dp, steps, base + off_theta,
                                        reinterpret_cast<const int*>(base + off_flag));
     PMC_CUDA_CHECK(cudaGetLastError());
     c->launches++;
     out->theta = base + off_theta;
     out->mma_cb = cb; out->mma_nb = nb; out->mma_nw = nw; out->mma_steps = steps; out->mma_kp = kp; out->mma_ys = k1m_row_stride(a.d);
   }
-  out->derived = base;
+  out->derived = base + off_rec;
   out->shift = base + off_shift;
   out->flag = reinterpret_cast<int*>(base + off_flag);
   out->base = a;
