@@ -79,6 +79,12 @@ int pmcb200_pack_record(int d,
  * weights_dev [n] are the per-sample weights used in sums_dev only (NULL = 1).
  * max_init is the starting value of the running maximum: -DBL_MAX normally, 0.0 to reproduce the reference
  * when dead columns (holding 0) take part in logsumexp2D's maximum (pmc.pyx:26-27, _regularize.pyx:72-76).
+ *
+ * Three kernel forms sit behind this call; which one works is decided on the device from the component parameters
+ * alone (never from the set of outputs, so log q has the same bits whichever outputs are requested): the FP64
+ * matrix-instruction form (9 <= kl <= 64, d >= 8, max_k |T_k (mu_k - c)|^2 <= 2e4), the DFMA form
+ * q = |T x' - b|^2 (|b| <= 1e4), and the exact-difference form y = x - mu_k for anything further out.
+ * Environment (tuning / comparison runs only, read per call): PMCB200_K1_FORM=dfma disables the first form.
  */
 int pmcb200_mixture_eval(pmcb200_ctx* ctx,
                          const double* x_dev, int64_t n, int64_t ldx, int d,
