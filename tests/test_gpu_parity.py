@@ -732,3 +732,42 @@ def test_k1_matrix_instruction_form(pm, orc, K, D, N, dof):
     np.testing.assert_allclose(res["mma"][1], res["dfma"][1], rtol=1e-12, atol=0)
     if K <= 64:
         assert not np.array_equal(res["mma"][1], res["dfma"][1])     # two different kernels did run
+
+
+def test_k1_matrix_instruction_form_tails_and_dead_components(pm, orc):
+    """DMMA form of K1 where its fused second pass differs most from a literal transcription: samples on a line
+    leaving the mixture (component log-pdfs run from ~-10 down to below -745, so exp(lp) passes through the subnormal
+    range and to zero) and dead components (weight 0: column stays 0, max_init = 0 path of pmc.pyx:26-27)."""
+    import torch
+    from pypmc_b200.density.mixture import create_gaussian_mixture
+    from pypmc_b200.density._eval import run_k1
+    from pypmc_b200.mix_adapt.pmc import gaussian_pmc
+    from pypmc_b200 import _lib
+    K, D, N = 12, 9, 4000
+    means, covs, w, x, sw = _synth(K, D, N, seed=77)
+    w[[2, 7]] = 0.0
+    w /= w.sum()
+    live = [k for k in range(K) if w[k] != 0]
+    direction = np.ones(D) / np.sqrt(D)
+    x[: N // 2] = means[0] + np.linspace(0.0, 60.0, N // 2)[:, None] * direction    # q/2 from 0 to beyond 745
+    comps = orc.Components(means, covs)
+    mix = create_gaussian_mixture(means, covs, w)
+    rho_ref, _ = orc.calculate_rho_rb(x, comps, w, live)
+    xd = torch.from_numpy(x).cuda()
+    rho = torch.zeros((N, K), dtype=torch.float64, device="cuda")
+    lq = torch.empty(N, dtype=torch.float64, device="cuda")
+    run_k1(xd, mix._packed(live), K, _lib.MODE_GAUSS, max_init=0.0, logq=lq, resp=rho)
+    got = rho.cpu().numpy()
+    assert np.isfinite(got).all()
+    assert (got[:, [2, 7]] == 0).all()
+    assert rel_err(got, rho_ref) < 1e-9
+    lq_ref, _ = orc.mixture_multi_evaluate(x, comps, w)
+    far = lq_ref < -700
+    assert far.any() and rel_err(lq.cpu().numpy()[~far], lq_ref[~far]) < TOL
+    # the update built on it agrees with the oracle's (weights, means)
+    new = gaussian_pmc(x, mix, weights=sw)
+    alpha, mu, cov = orc.pmc_moments(x, rho_ref, sample_weights=sw, live=live)
+    np.testing.assert_allclose(new.weights[live], alpha[live], rtol=1e-10, atol=1e-300)
+    for k in live:
+        np.testing.assert_allclose(new.components[k].mu, mu[k], rtol=1e-9)
+        assert mat_err(new.components[k].sigma, cov[k]) < 1e-9
