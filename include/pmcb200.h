@@ -82,7 +82,8 @@ int pmcb200_pack_record(int d,
  *
  * Three kernel forms sit behind this call; which one works is decided on the device from the component parameters
  * alone (never from the set of outputs, so log q has the same bits whichever outputs are requested): the FP64
- * matrix-instruction form (9 <= kl <= 64, d >= 8, max_k |T_k (mu_k - c)|^2 <= 2e4), the DFMA form
+ * matrix-instruction form (kl >= 9, d >= 8, max_k |T_k (mu_k - c)|^2 <= 2e4; in groups of components when their
+ * parameters exceed shared memory), the DFMA form
  * q = |T x' - b|^2 (|b| <= 1e4), and the exact-difference form y = x - mu_k for anything further out.
  * Environment (tuning / comparison runs only, read per call): PMCB200_K1_FORM=dfma disables the first form.
  */

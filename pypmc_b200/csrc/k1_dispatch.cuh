@@ -16,11 +16,12 @@ struct K1Launch {
   // matrix-instruction form (k1_mma_eval.cuh); mma_cb == 0: not offered for this launch
   const double* theta = nullptr;
   int mma_cb = 0, mma_nb = 0, mma_nw = 0, mma_steps = 0, mma_kp = 0, mma_ys = 0;
+  int mma_groups = 1;       // component groups of mma_kp (the last one may be shorter), one k1_mma_eval launch each
 };
 
 // k1_mma_eval<CB, NB> instantiations (k1_mma.cu): picks (CB, NB) for kl components of dimension d, 0 if the form does
 // not apply (too few components, theta + sample slices beyond the shared memory of an SM)
-bool k1_mma_config(int kl, int d, int* cb, int* nb, int* nw);
+bool k1_mma_config(int kl, int d, int* cb, int* nb, int* nw, int* groups);
 int k1_mma_launch(const K1Launch& l, int sm_count, cudaStream_t stream);
 
 // returns cudaError_t as int; grid <= #SMs (persistent CTAs, one per SM)

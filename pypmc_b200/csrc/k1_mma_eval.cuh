@@ -39,8 +39,14 @@ struct MmaArgs {
   const double* shift;    // [d]
   const int* flag;        // flag[0] != 0: exact-difference form runs; else flag[1] != 0: this form runs; else k1_fast_eval
   int steps;              // feature quads = ceil(F / 4)
-  int KP;                 // components padded to 8 CB
+  int KP;                 // components (of this group) padded to 8 CB
   int YS;                 // row stride (doubles) of the staged samples: >= d + 2 and == 4 (mod 16)
+  // Component groups: when theta of all components does not fit shared memory, the components are evaluated in
+  // `ngroups` launches of at most KP each (e.records / e.cols / e.kl / theta describe THIS group).  The running
+  // (max, weighted sum) of the log-sum-exp travels between the launches in rowstat; the last launch finishes log q
+  // and leaves (max, 1 / denominator) there for k1_finish, which then does the second pass (SECOND == false).
+  int group, ngroups;
+  double* rowstat;        // [n, 2]; null when ngroups == 1 and no k1_finish pass follows
 };
 
 __host__ __device__ inline int k1m_features(int d) { return 1 + d + d * (d + 1) / 2; }
@@ -204,9 +210,21 @@ __global__ void __launch_bounds__(NW * 32, 1) k1_mma_eval(const MmaArgs ma) {
     // ---- epilogue: lane holds q[sample 8 nb + g][component 8 cb + 2 tq + e] ----
     // Three phases over the whole tile (log-pdfs and their stores; maxima; exponentials and sums), so that the
     // NB x CB x 2 exponentials of a lane are independent instruction streams the scheduler can interleave.
-    double mx[NB];
+    double mx[NB], m_prev[NB], s_prev[NB];
 #pragma unroll
-    for (int nb = 0; nb < NB; ++nb) mx[nb] = a.max_init;
+    for (int nb = 0; nb < NB; ++nb) {
+      mx[nb] = a.max_init;
+      m_prev[nb] = a.max_init;
+      s_prev[nb] = 0.0;
+      if (ma.group > 0) {                                               // running (max, sum) of the earlier groups
+        const int64_t row = row0 + 8 * nb + g;
+        if (row < a.n) {
+          m_prev[nb] = ma.rowstat[2 * row];
+          s_prev[nb] = ma.rowstat[2 * row + 1];
+          mx[nb] = m_prev[nb];
+        }
+      }
+    }
 #pragma unroll
     for (int cb = 0; cb < CB; ++cb)
 #pragma unroll
@@ -266,7 +284,13 @@ __global__ void __launch_bounds__(NW * 32, 1) k1_mma_eval(const MmaArgs ma) {
         }
       }
     };
-    if (a.lp_out && a.mode != MODE_VB) store_pairs(a.lp_out, acc);
+    if constexpr (SECOND) {
+      if (a.lp_out && a.mode != MODE_VB) store_pairs(a.lp_out, acc);
+    } else {
+      // no fused second pass: like the DFMA forms, raw log-pdfs go to lp_out, or wait in resp_out for k1_finish
+      double* const scratch = a.lp_out ? a.lp_out : a.resp_out;
+      if (scratch) store_pairs(scratch, acc);
+    }
     // weighted log-sum-exp over the components (same value as _regularize.pyx:72-81 up to rounding)
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb) {
@@ -292,6 +316,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k1_mma_eval(const MmaArgs ma) {
     for (int nb = 0; nb < NB; ++nb) {
       sum[nb] += __shfl_xor_sync(0xffffffffu, sum[nb], 1);
       sum[nb] += __shfl_xor_sync(0xffffffffu, sum[nb], 2);
+      if (ma.group > 0) sum[nb] = fma(s_prev[nb], exp(m_prev[nb] - mx[nb]), sum[nb]);
     }
     // ---- per-sample results: lane tq == nb % 4 of the quad finishes sample nb and hands the quad what the
     //      second pass needs (the DFMA forms leave that pass to k1_finish; here the log-pdfs are still in registers) ----
@@ -303,20 +328,32 @@ __global__ void __launch_bounds__(NW * 32, 1) k1_mma_eval(const MmaArgs ma) {
       f0[nb] = 0.0;
       f1[nb] = 0.0;
       if (tq == (nb & 3)) {
-        const double lq = log(sum[nb]) + mx[nb];                        // _regularize.pyx:81
-        if (row < a.n) {
-          const double w_n = a.sw ? __ldg(a.sw + row) : 1.0;
-          part_w += w_n;
-          if (a.logq) a.logq[row] = lq;
-          if (a.mode != MODE_VB) part_a += w_n * lq;                    // pmc.pyx:388-391
-        }
-        if (second) {
-          if (a.mode != MODE_VB) {
-            f0[nb] = 1.0 / (exp(lq) + kTiny);                           // pmc.pyx:39-41
-            f1[nb] = exp(mx[nb]) * f0[nb];
-          } else {
-            f0[nb] = 1.0 / sum[nb];                                     // variational.pyx:728-755
-            f1[nb] = log(f0[nb]);
+        if (!SECOND && ma.group + 1 < ma.ngroups) {                     // more components to come
+          if (row < a.n) {
+            ma.rowstat[2 * row] = mx[nb];
+            ma.rowstat[2 * row + 1] = sum[nb];
+          }
+        } else {
+          const double lq = log(sum[nb]) + mx[nb];                      // _regularize.pyx:81
+          if (row < a.n) {
+            const double w_n = a.sw ? __ldg(a.sw + row) : 1.0;
+            part_w += w_n;
+            if (a.logq) a.logq[row] = lq;
+            if (a.mode != MODE_VB) part_a += w_n * lq;                  // pmc.pyx:388-391
+            if (!SECOND && ma.rowstat) {                                // for k1_finish
+              ma.rowstat[2 * row] = mx[nb];
+              ma.rowstat[2 * row + 1] = (a.mode != MODE_VB) ? 1.0 / (exp(lq) + kTiny)   // pmc.pyx:39-41
+                                                            : 1.0 / sum[nb];            // variational.pyx:728-755
+            }
+          }
+          if (second) {
+            if (a.mode != MODE_VB) {
+              f0[nb] = 1.0 / (exp(lq) + kTiny);                         // pmc.pyx:39-41
+              f1[nb] = exp(mx[nb]) * f0[nb];
+            } else {
+              f0[nb] = 1.0 / sum[nb];                                   // variational.pyx:728-755
+              f1[nb] = log(f0[nb]);
+            }
           }
         }
       }

@@ -74,12 +74,14 @@ __global__ void __launch_bounds__(128) k1_prepare(const double* __restrict__ rec
 // k1_mma_prepare: one CTA per (padded) component: theta_k from the derived record [T | -b | scalars].
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k1_mma_prepare(const double* __restrict__ derived, int kl, int KP, int d, int dp,
-                                                      int steps, double* __restrict__ theta, const int* __restrict__ flag) {
+                                                      int steps, double* __restrict__ theta_all, const int* __restrict__ flag) {
   if (flag[0] != 0 || flag[1] == 0) return;
-  const int k = blockIdx.x, tid = threadIdx.x;
+  // block b = (component group, slot in the group); theta of group g is [steps][KP][4] at g * steps * KP * 4
+  const int grp = blockIdx.x / KP, slot = blockIdx.x - grp * KP, k = grp * KP + slot, tid = threadIdx.x;
+  double* theta = theta_all + size_t(grp) * steps * KP * 4;
   const int nt = tri_len(dp), rl = record_len(dp), F = k1m_features(d);
   if (k >= kl) {                                                        // padding components: theta = 0
-    for (int f = tid; f < steps * 4; f += blockDim.x) theta[(size_t(f >> 2) * KP + k) * 4 + (f & 3)] = 0.0;
+    for (int f = tid; f < steps * 4; f += blockDim.x) theta[(size_t(f >> 2) * KP + slot) * 4 + (f & 3)] = 0.0;
     return;
   }
   __shared__ double Ts[PMC_MAX_DP * PMC_MAX_DP];                        // dense T, row stride dp
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(256) k1_mma_prepare(const double* __restrict__
       for (int u = r; u < d; ++u) m = fma(Ts[u * dp + r], Ts[u * dp + c], m);     // (T^T T)_rc, c <= r
       v = (r == c) ? m : 2.0 * m;
     }
-    theta[(size_t(f >> 2) * KP + k) * 4 + (f & 3)] = v;
+    theta[(size_t(f >> 2) * KP + slot) * 4 + (f & 3)] = v;
   }
 }
 
@@ -139,10 +141,11 @@ struct FinishArgs {
   double* resp_out;
   const int* flag;
   double* fin_partials;             // [gridDim.x] or null
+  int mma_fused;                    // the matrix-instruction form, if it ran, did the second pass itself
 };
 
 __global__ void __launch_bounds__(256, 4) k1_finish(const FinishArgs a) {
-  if (a.flag[0] != 0 || a.flag[1] != 0) return;      // exact-difference form / matrix-instruction form: pass already done
+  if (a.flag[0] != 0 || (a.flag[1] != 0 && a.mma_fused)) return;   // exact-difference form / fused DMMA form: pass already done
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int hw = (a.kl > 16) ? 32 : (a.kl > 8) ? 16 : (a.kl > 4) ? 8 : 4;
   const int per = 32 / hw, l_k = lane % hw, l_r = lane / hw;
@@ -202,8 +205,8 @@ __global__ void __launch_bounds__(256, 4) k1_finish(const FinishArgs a) {
 
 // sums[0] += sum_b fin_partials[b] in block order (VB: sum_n w_n sum_k r log r)
 __global__ void k1_reduce_finish(const double* __restrict__ fin_partials, int count, const int* __restrict__ flag,
-                                 double* __restrict__ sums) {
-  if (flag[0] != 0 || flag[1] != 0 || threadIdx.x != 0) return;
+                                 int mma_fused, double* __restrict__ sums) {
+  if (flag[0] != 0 || (flag[1] != 0 && mma_fused) || threadIdx.x != 0) return;
   double s = 0.0;
   for (int i = 0; i < count; ++i) s += fin_partials[i];
   sums[0] += s;

@@ -25,6 +25,10 @@ CASES = {
     "c3_eval": (10_000_000, 64, 20, _lib.MODE_GAUSS, ("logq",)),
     "c4_t_eval": (5_000_000, 16, 40, _lib.MODE_STUDENT_T, ("logq",)),
     "c4_t_rho": (5_000_000, 16, 40, _lib.MODE_STUDENT_T, ("logq", "resp", "aux")),
+    # beyond the shared-memory residency of theta: component groups (k1_mma_eval launched per group)
+    "k64d30_eval": (5_000_000, 64, 30, _lib.MODE_GAUSS, ("logq",)),
+    "k64d30_rho": (5_000_000, 64, 30, _lib.MODE_GAUSS, ("logq", "resp")),
+    "k32d40_t_eval": (5_000_000, 32, 40, _lib.MODE_STUDENT_T, ("logq",)),
 }
 
 
@@ -63,7 +67,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--reps", type=int, default=5)
-    ap.add_argument("--cases", default=",".join(CASES))
+    ap.add_argument("--cases", default="c2_eval,c2_rho,c3_vb,c3_eval,c4_t_eval,c4_t_rho")
     ap.add_argument("--kernels", default="k1,k2")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)

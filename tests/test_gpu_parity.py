@@ -679,9 +679,11 @@ def test_weigh_reuses_the_e_pass(pm):
 
 
 @pytest.mark.parametrize("K,D,N,dof", [(32, 30, 5003, None), (64, 20, 3001, None), (16, 40, 2000, 4.0), (12, 9, 1537, None),
-                                       (70, 11, 999, 5.0), (33, 13, 700, None), (9, 8, 257, 3.0)])
+                                       (70, 11, 999, 5.0), (33, 13, 700, None), (9, 8, 257, 3.0),
+                                       (64, 30, 1200, None), (32, 40, 900, 6.0), (96, 20, 800, None)])
 def test_k1_matrix_instruction_form(pm, orc, K, D, N, dof):
-    """The DMMA form of K1 (k1_mma_eval.cuh, the default for K >= 9, D >= 8) against the oracle, and against the
+    """The DMMA form of K1 (k1_mma_eval.cuh, the default for K >= 9, D >= 8; the last three shapes run it in
+    component groups because theta of all components exceeds shared memory) against the oracle, and against the
     DFMA form (PMCB200_K1_FORM=dfma, read per call) to rounding: log-pdfs, log q, rho / gamma, a component subset
     (non-contiguous output columns) and weighted sums."""
     import torch
@@ -730,7 +732,7 @@ def test_k1_matrix_instruction_form(pm, orc, K, D, N, dof):
             os.environ["PMCB200_K1_FORM"] = old
     np.testing.assert_allclose(res["mma"][0], res["dfma"][0], rtol=1e-12, atol=0)
     np.testing.assert_allclose(res["mma"][1], res["dfma"][1], rtol=1e-12, atol=0)
-    if K <= 64:
+    if K != 70:                                                      # (70, 11): padding too wasteful, DFMA form either way
         assert not np.array_equal(res["mma"][1], res["dfma"][1])     # two different kernels did run
 
 
