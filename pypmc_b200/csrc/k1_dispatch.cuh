@@ -13,15 +13,21 @@ struct K1Launch {
   const double* shift;      // [DP]
   const int* flag;
   double* rowstat;          // [n, 2] for k1_finish, or null
-  // matrix-instruction form (k1_mma_eval.cuh); mma_cb == 0: not offered for this launch
+  // matrix-instruction form (k1_mma_eval.cuh); mma.groups == 0: not offered for this launch
+  struct MmaPlan {
+    static constexpr int kMaxGroups = 16;
+    int groups = 0;                       // component groups, one k1_mma_eval launch each
+    int k0[kMaxGroups] = {}, count[kMaxGroups] = {}, cb[kMaxGroups] = {};   // first component, components, blocks of 8
+    size_t theta_off[kMaxGroups] = {};    // offset (doubles) of the group's theta [steps][8 cb][4]
+    size_t theta_len = 0;
+    int steps = 0, ys = 0;
+  } mma;
   const double* theta = nullptr;
-  int mma_cb = 0, mma_nb = 0, mma_nw = 0, mma_steps = 0, mma_kp = 0, mma_ys = 0;
-  int mma_groups = 1;       // component groups of mma_kp (the last one may be shorter), one k1_mma_eval launch each
 };
 
-// k1_mma_eval<CB, NB> instantiations (k1_mma.cu): picks (CB, NB) for kl components of dimension d, 0 if the form does
-// not apply (too few components, theta + sample slices beyond the shared memory of an SM)
-bool k1_mma_config(int kl, int d, int* cb, int* nb, int* nw, int* groups);
+// Plans the component groups of the matrix-instruction form for kl components of dimension d; false if the form
+// does not apply (too few components, tiny D, or a grouping that would pad the component count by more than 20 %).
+bool k1_mma_plan(int kl, int d, K1Launch::MmaPlan* plan);
 int k1_mma_launch(const K1Launch& l, int sm_count, cudaStream_t stream);
 
 // returns cudaError_t as int; grid <= #SMs (persistent CTAs, one per SM)

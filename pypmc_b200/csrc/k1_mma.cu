@@ -1,4 +1,4 @@
-// K1 matrix-instruction form: instantiations and launch (k1_mma_eval.cuh)
+// K1 matrix-instruction form: instantiations, component-group plan and launch (k1_mma_eval.cuh)
 #include "k1_dispatch.cuh"
 
 #include <algorithm>
@@ -8,37 +8,39 @@ namespace pmc {
 
 constexpr size_t kSmemLimit = 227 * 1024;
 
-// (CB, NB, NW) variants compiled in.  16 warps (four per scheduler) measured best: a warp issues at most one DMMA
-// per ~32 clk, the pipe takes one per 16, and a warp in its epilogue issues none (C2: 8 warps 11.3 ms, 12 warps
-// 10.7 ms, 16 warps 10.5 ms; C3: (8,4,8) 12.3 ms, (8,2,12) 11.5 ms, (8,2,16) 11.8 ms with spills, (8,1,16) 11.1 ms).
-static bool have_variant(int cb, int nb, int nw) {
-  return (cb == 2 && nb == 2 && nw == 16) || (cb == 4 && nb == 2 && nw == 16) || (cb == 8 && nb == 1 && nw == 16) ||
-         (cb == 4 && nb == 4 && nw == 8) || (cb == 8 && nb == 2 && nw == 12);
-}
+// Tile variant per component-block count CB: 16 warps (four per scheduler) measured best -- a warp issues at most
+// one DMMA per ~32 clk, the pipe takes one per 16, and a warp in its epilogue issues none (C2: 8 warps 11.3 ms, 12
+// warps 10.7 ms, 16 warps 10.5 ms; C3: (8,4,8) 12.3 ms, (8,2,12) 11.5 ms, (8,2,16) 11.8 ms with spills, (8,1,16)
+// 11.1 ms; profiles/r01f_k1_mma_variants.md).  NB = 2 sample blocks per warp while the accumulators leave room.
+static int nb_for(int cb) { return cb <= 5 ? 2 : 1; }
+constexpr int kWarps = 16;
 
-bool k1_mma_config(int kl, int d, int* cb, int* nb, int* nw, int* groups) {
+bool k1_mma_plan(int kl, int d, K1Launch::MmaPlan* plan) {
   if (kl < 9 || d < 8) return false;                  // few components / tiny D: the DFMA form's epilogue-bound regime
-  int en = 0, ew = 0;
-  if (const char* env = getenv("PMCB200_K1_MMA_CFG"))        // "NB,NW": tuning runs
-    if (sscanf(env, "%d,%d", &en, &ew) != 2) en = ew = 0;
-  // Largest component block count whose theta (all feature quads x 8 CB components) fits shared memory beside the
-  // sample slices; more components than that are evaluated in groups (one launch each, log-sum-exp carried in
-  // rowstat).  Padding of the last group is issued work: accept a grouping only while the padded count stays within
-  // 15 % of kl -- beyond that the DFMA form (70 %) is the better choice.
-  const int first = (kl <= 16) ? 2 : (kl <= 32) ? 4 : 8;
-  for (int c = first; c >= 2; c /= 2) {
-    int n = (c == 8) ? 1 : 2, w = 16;
-    if (have_variant(c, en, ew)) { n = en; w = ew; }
-    if (k1m_smem_bytes(d, 8 * c, n, w) > kSmemLimit) continue;
-    const int g = (kl + 8 * c - 1) / (8 * c);
-    if (g > 1 && (g * 8 * c * 100 > kl * 115 || (c < 4 && d < 33))) continue;   // (CB = 2 is LDS-bound: only where DFMA is weak)
-    *cb = c;
-    *nb = n;
-    *nw = w;
-    *groups = g;
-    return true;
+  int cbmax = 0;                                      // largest block count whose theta fits beside the sample slices
+  for (int c = 8; c >= 2; --c)
+    if (k1m_smem_bytes(d, 8 * c, nb_for(c), kWarps) <= kSmemLimit) { cbmax = c; break; }
+  if (cbmax == 0) return false;
+  const int full = kl / (8 * cbmax), rest = kl - full * 8 * cbmax;
+  const int cb_rest = rest ? std::max(2, (rest + 7) / 8) : 0;
+  const int groups = full + (rest ? 1 : 0), slots = full * 8 * cbmax + 8 * cb_rest;
+  // padding is issued work: beyond 20 % the DFMA form (70 % of the pipe) wins; CB = 2 groups are bound by the
+  // shared-memory pipe (74 %) and only pay where the DFMA form is weak (D > 32)
+  if (groups > K1Launch::MmaPlan::kMaxGroups || slots * 100 > kl * 120) return false;
+  if (groups > 1 && cbmax < 4 && d < 33) return false;
+  plan->groups = groups;
+  plan->steps = (k1m_features(d) + 3) / 4;
+  plan->ys = k1m_row_stride(d);
+  size_t off = 0;
+  for (int g = 0; g < groups; ++g) {
+    plan->k0[g] = g * 8 * cbmax;
+    plan->cb[g] = (g < full) ? cbmax : cb_rest;
+    plan->count[g] = (g < full) ? 8 * cbmax : rest;
+    plan->theta_off[g] = off;
+    off += size_t(plan->steps) * 8 * plan->cb[g] * 4;
   }
-  return false;
+  plan->theta_len = off;
+  return true;
 }
 
 template <int CB, int NB, int NW, bool SECOND>
@@ -58,22 +60,24 @@ static int launch(const MmaArgs& ma, int sm_count, size_t smem, cudaStream_t str
 }
 
 int k1_mma_launch(const K1Launch& l, int sm_count, cudaStream_t stream) {
-  const size_t smem = k1m_smem_bytes(l.base.d, l.mma_kp, l.mma_nb, l.mma_nw);
+  const K1Launch::MmaPlan& p = l.mma;
   const bool second_pass = (l.base.resp_out != nullptr) || (l.base.mode == MODE_VB && l.base.lp_out != nullptr);
-  const bool second = second_pass && l.mma_groups == 1;              // fused; with groups k1_finish does it
+  const bool second = second_pass && p.groups == 1;                  // fused; with groups k1_finish does it
   const int rl = record_len((l.base.d + 1) & ~1);
-  for (int g = 0; g < l.mma_groups; ++g) {
-    MmaArgs ma{l.base, l.theta + size_t(g) * l.mma_steps * l.mma_kp * 4, l.shift, l.flag, l.mma_steps, l.mma_kp, l.mma_ys,
-               g, l.mma_groups, l.rowstat};
-    ma.e.records = l.derived + size_t(g) * l.mma_kp * rl;
-    ma.e.cols = l.base.cols + g * l.mma_kp;
-    ma.e.kl = std::min(l.mma_kp, l.base.kl - g * l.mma_kp);
-    if (g + 1 < l.mma_groups) ma.e.partials = nullptr;               // the sums belong to the last launch
+  for (int g = 0; g < p.groups; ++g) {
+    const int cb = p.cb[g], nb = nb_for(cb);
+    MmaArgs ma{l.base, l.theta + p.theta_off[g], l.shift, l.flag, p.steps, 8 * cb, p.ys, g, p.groups, l.rowstat};
+    ma.e.records = l.derived + size_t(p.k0[g]) * rl;
+    ma.e.cols = l.base.cols + p.k0[g];
+    ma.e.kl = p.count[g];
+    if (g + 1 < p.groups) ma.e.partials = nullptr;                   // the sums belong to the last launch
+    const size_t smem = k1m_smem_bytes(l.base.d, 8 * cb, nb, kWarps);
     int rc = int(cudaErrorInvalidValue);
-#define PMC_K1M_CASE(CBV, NBV, NWV)                                                             \
-    if (l.mma_cb == CBV && l.mma_nb == NBV && l.mma_nw == NWV)                                  \
-      rc = second ? launch<CBV, NBV, NWV, true>(ma, sm_count, smem, stream) : launch<CBV, NBV, NWV, false>(ma, sm_count, smem, stream);
-    PMC_K1M_CASE(2, 2, 16) PMC_K1M_CASE(4, 2, 16) PMC_K1M_CASE(8, 1, 16) PMC_K1M_CASE(4, 4, 8) PMC_K1M_CASE(8, 2, 12)
+#define PMC_K1M_CASE(CBV, NBV)                                                                  \
+    if (cb == CBV)                                                                              \
+      rc = second ? launch<CBV, NBV, kWarps, true>(ma, sm_count, smem, stream) : launch<CBV, NBV, kWarps, false>(ma, sm_count, smem, stream);
+    PMC_K1M_CASE(2, 2) PMC_K1M_CASE(3, 2) PMC_K1M_CASE(4, 2) PMC_K1M_CASE(5, 2) PMC_K1M_CASE(6, 1) PMC_K1M_CASE(7, 1)
+    PMC_K1M_CASE(8, 1)
 #undef PMC_K1M_CASE
     if (rc != 0) return rc;
   }

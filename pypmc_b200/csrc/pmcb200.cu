@@ -268,24 +268,27 @@ static int eval_prepare(pmcb200_ctx* c, DevBuf& prep, const EvalArgs& a, cudaStr
   const size_t off_flag = 0, off_rec = 2, off_shift = off_rec + size_t(a.kl) * rl, off_part = off_shift + PMC_MAX_DP;
   const size_t off_fin = off_part + n_part, n_fin = size_t(c->sm_count) * 8;
   // matrix-instruction form: offered unless PMCB200_K1_FORM=dfma (comparison runs), k1_prepare has the last word
-  int cb = 0, nb = 0, nw = 0, groups = 1;
+  K1Launch::MmaPlan plan;
   const char* form_env = getenv("PMCB200_K1_FORM");
-  const bool want_mma = !(form_env && std::string(form_env) == "dfma") && k1_mma_config(a.kl, a.d, &cb, &nb, &nw, &groups);
-  const int steps = (k1m_features(a.d) + 3) / 4, kp = 8 * cb;
-  const size_t off_theta = off_fin + n_fin, n_theta = want_mma ? size_t(groups) * steps * kp * 4 : 0;
+  const bool want_mma = !(form_env && std::string(form_env) == "dfma") && k1_mma_plan(a.kl, a.d, &plan);
+  const size_t off_theta = off_fin + n_fin, n_theta = want_mma ? plan.theta_len : 0;
   if (int rc = ensure(prep, (off_theta + n_theta) * sizeof(double))) return rc;
   double* base = static_cast<double*>(prep.p);
   k1_prepare<<<a.kl, 128, 0, st>>>(a.records, a.kl, dp, base + off_rec, base + off_shift, reinterpret_cast<int*>(base + off_flag),
                                 base + off_part, int(n_part), want_mma ? 1 : 0);
   PMC_CUDA_CHECK(cudaGetLastError());
   c->launches++;
+  out->mma = K1Launch::MmaPlan();
   if (want_mma) {
-    k1_mma_prepare<<<groups * kp, 256, 0, st>>>(base + off_rec, a.kl, kp, a.d, dp, steps, base + off_theta,
-                                       reinterpret_cast<const int*>(base + off_flag));
-    PMC_CUDA_CHECK(cudaGetLastError());
-    c->launches++;
+    for (int g = 0; g < plan.groups; ++g) {            // theta per component group
+      k1_mma_prepare<<<8 * plan.cb[g], 256, 0, st>>>(base + off_rec + size_t(plan.k0[g]) * rl, plan.count[g], 8 * plan.cb[g],
+                                                     a.d, dp, plan.steps, base + off_theta + plan.theta_off[g],
+                                                     reinterpret_cast<const int*>(base + off_flag));
+      PMC_CUDA_CHECK(cudaGetLastError());
+      c->launches++;
+    }
     out->theta = base + off_theta;
-    out->mma_cb = cb; out->mma_nb = nb; out->mma_nw = nw; out->mma_groups = groups; out->mma_steps = steps; out->mma_kp = kp; out->mma_ys = k1m_row_stride(a.d);
+    out->mma = plan;
   }
   out->derived = base + off_rec;
   out->shift = base + off_shift;
@@ -305,7 +308,7 @@ static int eval_launch(pmcb200_ctx* c, const K1Launch& prep, DevBuf& rowbuf, con
   l.base.partials = sums_dev ? partials : nullptr;
   const bool second_pass = (a0.resp_out != nullptr) || (a0.mode == MODE_VB && a0.lp_out != nullptr);
   l.rowstat = nullptr;
-  if (second_pass || l.mma_groups > 1) {
+  if (second_pass || l.mma.groups > 1) {
     if (int rc = ensure(rowbuf, size_t(a0.n) * 2 * sizeof(double))) return rc;
     l.rowstat = static_cast<double*>(rowbuf.p);
   }
@@ -313,13 +316,13 @@ static int eval_launch(pmcb200_ctx* c, const K1Launch& prep, DevBuf& rowbuf, con
   const int ts = k1_tile_rows(dp);
   const int64_t tiles = (a0.n + ts - 1) / ts;
   const int grid = int(std::min<int64_t>(tiles, c->sm_count));
-  if (l.mma_cb > 0) {
+  if (l.mma.groups > 0) {
     const int em = k1_mma_launch(l, c->sm_count, st);
     if (em != 0) {
       set_last_error(std::string("k1 mma launch: ") + cudaGetErrorString(cudaError_t(em)));
       return 1;
     }
-    c->launches += l.mma_groups;
+    c->launches += l.mma.groups;
   }
   const int e = k1_launch(dp, l, grid, st);
   if (e != 0) {
@@ -336,7 +339,7 @@ static int eval_launch(pmcb200_ctx* c, const K1Launch& prep, DevBuf& rowbuf, con
     f.records = l.derived; f.cols = a0.cols; f.rowstat = l.rowstat; f.sw = a0.sw;
     f.scratch = a0.lp_out ? a0.lp_out : a0.resp_out; f.lp_out = a0.lp_out; f.resp_out = a0.resp_out;
     f.flag = l.flag; f.fin_partials = fin_sum ? fin_partials : nullptr;
-    f.mma_fused = (l.mma_groups == 1) ? 1 : 0;
+    f.mma_fused = (l.mma.groups == 1) ? 1 : 0;
     k1_finish<<<fin_grid, 256, 0, st>>>(f);
     PMC_CUDA_CHECK(cudaGetLastError());
     c->launches++;
@@ -347,7 +350,7 @@ static int eval_launch(pmcb200_ctx* c, const K1Launch& prep, DevBuf& rowbuf, con
     PMC_CUDA_CHECK(cudaGetLastError());
     c->launches++;
     if (fin_sum) {
-      k1_reduce_finish<<<1, 32, 0, st>>>(fin_partials, fin_grid, l.flag, (l.mma_groups == 1) ? 1 : 0, sums_dev);
+      k1_reduce_finish<<<1, 32, 0, st>>>(fin_partials, fin_grid, l.flag, (l.mma.groups == 1) ? 1 : 0, sums_dev);
       PMC_CUDA_CHECK(cudaGetLastError());
       c->launches++;
     }

@@ -678,13 +678,14 @@ def test_weigh_reuses_the_e_pass(pm):
         np.testing.assert_array_equal(other.weights, ref2.weights)
 
 
-@pytest.mark.parametrize("K,D,N,dof", [(32, 30, 5003, None), (64, 20, 3001, None), (16, 40, 2000, 4.0), (12, 9, 1537, None),
-                                       (70, 11, 999, 5.0), (33, 13, 700, None), (9, 8, 257, 3.0),
+@pytest.mark.parametrize("K,D,N,dof", [(32, 30, 5003, None), (64, 20, 3001, None), (16, 40, 2000, 4.0), (14, 9, 1537, None),
+                                       (70, 11, 999, 5.0), (35, 13, 700, None), (15, 8, 257, 3.0), (21, 30, 600, None),
+                                       (44, 12, 500, 7.0), (52, 10, 400, None), (38, 16, 450, None),
                                        (64, 30, 1200, None), (32, 40, 900, 6.0), (96, 20, 800, None)])
 def test_k1_matrix_instruction_form(pm, orc, K, D, N, dof):
-    """The DMMA form of K1 (k1_mma_eval.cuh, the default for K >= 9, D >= 8; the last three shapes run it in
-    component groups because theta of all components exceeds shared memory) against the oracle, and against the
-    DFMA form (PMCB200_K1_FORM=dfma, read per call) to rounding: log-pdfs, log q, rho / gamma, a component subset
+    """The DMMA form of K1 (k1_mma_eval.cuh, the default for K >= 9, D >= 8 when the component count pads to blocks of
+    8 within 20 %; every block count 2..8 is covered, (70, 11) and the last three shapes run in component groups
+    because theta of all components exceeds shared memory) against the oracle, and against the DFMA form (PMCB200_K1_FORM=dfma, read per call) to rounding: log-pdfs, log q, rho / gamma, a component subset
     (non-contiguous output columns) and weighted sums."""
     import torch
     from pypmc_b200.density.mixture import create_gaussian_mixture, create_t_mixture
@@ -732,8 +733,7 @@ def test_k1_matrix_instruction_form(pm, orc, K, D, N, dof):
             os.environ["PMCB200_K1_FORM"] = old
     np.testing.assert_allclose(res["mma"][0], res["dfma"][0], rtol=1e-12, atol=0)
     np.testing.assert_allclose(res["mma"][1], res["dfma"][1], rtol=1e-12, atol=0)
-    if K != 70:                                                      # (70, 11): padding too wasteful, DFMA form either way
-        assert not np.array_equal(res["mma"][1], res["dfma"][1])     # two different kernels did run
+    assert not np.array_equal(res["mma"][1], res["dfma"][1])         # two different kernels did run
 
 
 def test_k1_matrix_instruction_form_tails_and_dead_components(pm, orc):
