@@ -29,6 +29,12 @@ CASES = {
     "k64d30_eval": (5_000_000, 64, 30, _lib.MODE_GAUSS, ("logq",)),
     "k64d30_rho": (5_000_000, 64, 30, _lib.MODE_GAUSS, ("logq", "resp")),
     "k32d40_t_eval": (5_000_000, 32, 40, _lib.MODE_STUDENT_T, ("logq",)),
+    # component counts between the block sizes (CB = 3, 5, 6, 7; 48 = 32 + 16 in two groups)
+    "k21d30_eval": (5_000_000, 21, 30, _lib.MODE_GAUSS, ("logq",)),
+    "k40d20_eval": (5_000_000, 40, 20, _lib.MODE_GAUSS, ("logq",)),
+    "k48d30_eval": (5_000_000, 48, 30, _lib.MODE_GAUSS, ("logq",)),
+    "k56d20_eval": (5_000_000, 56, 20, _lib.MODE_GAUSS, ("logq",)),
+    "k17d30_eval": (5_000_000, 17, 30, _lib.MODE_GAUSS, ("logq",)),
 }
 
 
