@@ -11,15 +11,18 @@ constexpr size_t kSmemLimit = 227 * 1024;
 // Tile variant per component-block count CB: 16 warps (four per scheduler) measured best -- a warp issues at most
 // one DMMA per ~32 clk, the pipe takes one per 16, and a warp in its epilogue issues none (C2: 8 warps 11.3 ms, 12
 // warps 10.7 ms, 16 warps 10.5 ms; C3: (8,4,8) 12.3 ms, (8,2,12) 11.5 ms, (8,2,16) 11.8 ms with spills, (8,1,16)
-// 11.1 ms; profiles/r01f_k1_mma_variants.md).  NB = 2 sample blocks per warp while the accumulators leave room.
-static int nb_for(int cb) { return cb <= 5 ? 2 : 1; }
+// 11.1 ms; profiles/r01f_k1_mma_variants.md).  NB = 2 sample blocks per warp while the accumulators leave room: always
+// for the eval-only instantiation (theta fragments then feed two DMMAs each: K=56, D=20 4.63 vs 4.99 ms), up to CB = 5
+// with the fused second pass, whose second register array would spill beyond that (C3 VB 17.8 vs 13.7 ms).  The
+// per-sample arithmetic does not depend on NB, so both instantiations give the same log q bit for bit.
+static int nb_for(int cb, bool second) { return (cb <= 5 || !second) ? 2 : 1; }
 constexpr int kWarps = 16;
 
 bool k1_mma_plan(int kl, int d, K1Launch::MmaPlan* plan) {
   if (kl < 9 || d < 8) return false;                  // few components / tiny D: the DFMA form's epilogue-bound regime
   int cbmax = 0;                                      // largest block count whose theta fits beside the sample slices
   for (int c = 8; c >= 2; --c)
-    if (k1m_smem_bytes(d, 8 * c, nb_for(c), kWarps) <= kSmemLimit) { cbmax = c; break; }
+    if (k1m_smem_bytes(d, 8 * c, 2, kWarps) <= kSmemLimit) { cbmax = c; break; }
   if (cbmax == 0) return false;
   const int full = kl / (8 * cbmax), rest = kl - full * 8 * cbmax;
   const int cb_rest = rest ? std::max(2, (rest + 7) / 8) : 0;
@@ -65,7 +68,7 @@ int k1_mma_launch(const K1Launch& l, int sm_count, cudaStream_t stream) {
   const bool second = second_pass && p.groups == 1;                  // fused; with groups k1_finish does it
   const int rl = record_len((l.base.d + 1) & ~1);
   for (int g = 0; g < p.groups; ++g) {
-    const int cb = p.cb[g], nb = nb_for(cb);
+    const int cb = p.cb[g], nb = nb_for(cb, second);
     MmaArgs ma{l.base, l.theta + p.theta_off[g], l.shift, l.flag, p.steps, 8 * cb, p.ys, g, p.groups, l.rowstat};
     ma.e.records = l.derived + size_t(p.k0[g]) * rl;
     ma.e.cols = l.base.cols + p.k0[g];
@@ -73,11 +76,12 @@ int k1_mma_launch(const K1Launch& l, int sm_count, cudaStream_t stream) {
     if (g + 1 < p.groups) ma.e.partials = nullptr;                   // the sums belong to the last launch
     const size_t smem = k1m_smem_bytes(l.base.d, 8 * cb, nb, kWarps);
     int rc = int(cudaErrorInvalidValue);
-#define PMC_K1M_CASE(CBV, NBV)                                                                  \
+#define PMC_K1M_CASE(CBV, NB_EVAL, NB_SECOND)                                                   \
     if (cb == CBV)                                                                              \
-      rc = second ? launch<CBV, NBV, kWarps, true>(ma, sm_count, smem, stream) : launch<CBV, NBV, kWarps, false>(ma, sm_count, smem, stream);
-    PMC_K1M_CASE(2, 2) PMC_K1M_CASE(3, 2) PMC_K1M_CASE(4, 2) PMC_K1M_CASE(5, 2) PMC_K1M_CASE(6, 1) PMC_K1M_CASE(7, 1)
-    PMC_K1M_CASE(8, 1)
+      rc = second ? launch<CBV, NB_SECOND, kWarps, true>(ma, sm_count, smem, stream)            \
+                  : launch<CBV, NB_EVAL, kWarps, false>(ma, sm_count, smem, stream);
+    PMC_K1M_CASE(2, 2, 2) PMC_K1M_CASE(3, 2, 2) PMC_K1M_CASE(4, 2, 2) PMC_K1M_CASE(5, 2, 2) PMC_K1M_CASE(6, 2, 1)
+    PMC_K1M_CASE(7, 2, 1) PMC_K1M_CASE(8, 2, 1)
 #undef PMC_K1M_CASE
     if (rc != 0) return rc;
   }

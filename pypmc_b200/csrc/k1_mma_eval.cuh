@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k1_mma_eval(const MmaArgs ma) {
   const EvalArgs& a = ma.e;
   if (ma.flag[0] != 0 || ma.flag[1] == 0) return;
   constexpr int RW = 8 * NB, TS = RW * NW, KP = 8 * CB;
-  constexpr int UNR = (CB * NB <= 4) ? 4 : 2;          // feature quads per loop body (at least 16 DMMAs)
+  constexpr int UNR = (CB * NB <= 4) ? 4 : (CB * NB >= 12) ? 1 : 2;   // feature quads per loop body (about 16 DMMAs)
   const int D = a.d, YS = ma.YS, steps = ma.steps;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
