@@ -498,6 +498,15 @@ def test_empty_and_single_row_inputs(pm):
     assert one.shape == (1,) and one[0] == pytest.approx(mix.multi_evaluate(x)[0], rel=1e-14)
     wd = torch.from_numpy(sw).cuda()
     assert perp(wd) == pytest.approx(perp(sw), rel=1e-12) and ess(wd) == pytest.approx(ess(sw), rel=1e-12)
+    # the same through the matrix-instruction form of K1 (K >= 9, D >= 8): N = 1, N = 7 (less than one 8-row block),
+    # and bit-identical rows whatever their position in a tile (a row's arithmetic must not depend on its neighbours)
+    means, covs, w, x, sw = _synth(16, 10, 1000, seed=3)
+    mix = create_gaussian_mixture(means, covs, w)
+    full = mix.multi_evaluate(x)
+    assert mix.multi_evaluate(np.empty((0, 10))).shape == (0,)
+    np.testing.assert_array_equal(mix.multi_evaluate(x[:1]), full[:1])
+    np.testing.assert_array_equal(mix.multi_evaluate(x[:7]), full[:7])
+    np.testing.assert_array_equal(mix.multi_evaluate(x[333:777]), full[333:777])
 
 
 def test_full_size_update_invariants(pm):
