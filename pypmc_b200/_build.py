@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(CSRC, "libpmcb200.so")
-SOURCES = ["pmcb200.cu", "k1_inst_0.cu", "k1_inst_1.cu", "k1_inst_2.cu", "k1_inst_3.cu", "k1_mma.cu"]
+SOURCES = ["pmcb200.cu", "k1_inst_0.cu", "k1_inst_1.cu", "k1_inst_2.cu", "k1_inst_3.cu", "k1_mma.cu", "k2_inst.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-I", INCLUDE,

@@ -370,6 +370,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_suffstats(const StatsArgs a)
   }
 }
 
+#ifndef PMC_K2_TEMPLATE_ONLY   // (k2_inst.cu instantiates more tile shapes of the template above and needs only that)
 // ---------------------------------------------------------------------------------------------
 // Column sums that go with gamma (Student-t): A_k = sum_n w_n rho_nk and L_k = sum_n w_n rho_nk ln(gamma_nk)
 // (the N-sized part of the dof condition, pmc.pyx:654-691).  A streaming pass of its own: in the producer warps of
@@ -432,5 +433,10 @@ __global__ void k2_reduce_partials(const double* __restrict__ partial, int nbloc
   for (int b = 0; b < nblocks; ++b) s += partial[size_t(b) * len + e];
   out[e] = s;
 }
+
+#endif  // PMC_K2_TEMPLATE_ONLY
+
+// k2_suffstats<CB, FB> for CB = 3, 5, 6, 7 (k2_inst.cu); returns 2 when (cb, fb) is not instantiated
+int k2_launch_extra(int cb, int fb, const StatsArgs& a, dim3 grid, size_t smem, cudaStream_t stream);
 
 }  // namespace pmc

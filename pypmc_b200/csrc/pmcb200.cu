@@ -77,6 +77,11 @@ __global__ void k1_reduce_sums(double* __restrict__ partials, int count, double*
 
 using namespace pmc;
 
+// K2: component-block counts 2..8 (true) or powers of two only (false) by default; see pmcb200_suffstats
+#ifndef K2_FINE_BLOCKS_DEFAULT
+#define K2_FINE_BLOCKS_DEFAULT 0
+#endif
+
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
@@ -405,8 +410,19 @@ int pmcb200_suffstats(pmcb200_ctx* c, const double* x, int64_t n, int64_t ldx, i
   const bool mma = !(form_env && std::string(form_env) == "dfma");
   int gy, cbw = 0, fbw = 0;
   if (mma) {
-    const int cb_total = a.KP / 8;                       // component blocks of 8 (KP is a multiple of 16)
-    cbw = (cb_total <= 2) ? 2 : (cb_total <= 4) ? 4 : 8; // per-warp tile CB x FB, at most 32 C tiles (64 accumulators)
+    // component blocks of 8 per warp tile (CB x FB, at most 32 C tiles = 64 accumulators): the blocks that hold
+    // components, split evenly over the CTAs that share them; PMCB200_K2_BLOCKS=pow2 restores the earlier choice
+    // (next power of two), kept for comparison runs
+    static const char* blocks_env = getenv("PMCB200_K2_BLOCKS");
+    const bool fine = K2_FINE_BLOCKS_DEFAULT ? !(blocks_env && std::string(blocks_env) == "pow2")
+                                             : (blocks_env && std::string(blocks_env) == "fine");
+    int cb_total = (k + 7) / 8, cchunks = (cb_total + 7) / 8;
+    cbw = std::max(2, (cb_total + cchunks - 1) / cchunks);
+    if (!fine) {
+      cb_total = a.KP / 8;
+      cbw = (cb_total <= 2) ? 2 : (cb_total <= 4) ? 4 : 8;
+      cchunks = (cb_total + cbw - 1) / cbw;
+    }
     a.nFB = (F + 7) / 8;
     const int nw = K2_CONSUMERS / 32, fb_max = 32 / cbw;
     a.fchunks = (a.nFB + nw * fb_max - 1) / (nw * fb_max);
@@ -414,13 +430,14 @@ int pmcb200_suffstats(pmcb200_ctx* c, const double* x, int64_t n, int64_t ldx, i
     // instantiated FB values per CB (the smallest one >= need is used; blocks beyond the warp's share are zero work
     // that is still issued, so a tight FB matters: D=40 gives 108 blocks = 13.5 per warp -> FB 14, not 16)
     static const int fb2[] = {2, 4, 6, 8, 10, 12, 14, 16}, fb4[] = {1, 2, 3, 4, 5, 6, 7, 8}, fb8[] = {1, 2, 3, 4};
-    const int* tab = (cbw == 2) ? fb2 : (cbw == 4) ? fb4 : fb8;
-    const int ntab = (cbw == 2) ? 8 : (cbw == 4) ? 8 : 4;
+    static const int fb3[] = {2, 4, 6, 8, 10}, fb5[] = {2, 3, 4, 5, 6}, fb6[] = {2, 3, 4, 5}, fb7[] = {2, 3, 4};
+    const int* tab = (cbw == 2) ? fb2 : (cbw == 3) ? fb3 : (cbw == 4) ? fb4 : (cbw == 5) ? fb5 : (cbw == 6) ? fb6 : (cbw == 7) ? fb7 : fb8;
+    const int ntab = (cbw == 2) ? 8 : (cbw == 3) ? 5 : (cbw == 4) ? 8 : (cbw == 5) ? 5 : (cbw == 6) ? 4 : (cbw == 7) ? 3 : 4;
     fbw = tab[ntab - 1];
     for (int i = 0; i < ntab; ++i)
       if (tab[i] >= need) { fbw = tab[i]; break; }
     a.fbw = fbw;
-    gy = a.fchunks * ((cb_total + cbw - 1) / cbw);
+    gy = a.fchunks * cchunks;
     a.DP4 = ((d + 2 + 3) / 4) * 4;                       // [y, 1, 0...]: always at least one zero column (index d+1)
     a.VS = a.KP + 4;                                     // row strides = 4 (mod 16) doubles: the 8 x 4 fragment loads of a
     a.YS = ((a.DP4 + 11) / 16) * 16 + 4;                 // half-warp then touch 16 different 8-byte banks
@@ -464,6 +481,10 @@ int pmcb200_suffstats(pmcb200_ctx* c, const double* x, int64_t n, int64_t ldx, i
   PMC_K2_CASE(4, 6, 14) PMC_K2_CASE(4, 7, 15) PMC_K2_CASE(4, 8, 16)
   PMC_K2_CASE(8, 1, 17) PMC_K2_CASE(8, 2, 18) PMC_K2_CASE(8, 3, 19) PMC_K2_CASE(8, 4, 20)
 #undef PMC_K2_CASE
+  if (rc == 2 && mma) {
+    rc = k2_launch_extra(cbw, fbw, a, dim3(gx, gy), smem, st);
+    if (rc == 1) set_last_error("suffstats: launch of a k2_inst.cu instantiation failed");
+  }
   PMC_REQUIRE(rc != 2, "suffstats: no kernel instantiation for this tile shape");
   if (rc) return rc;
   k2_reduce_partials<<<unsigned((len + 255) / 256), 256, 0, st>>>(a.partial, gx, len, out);

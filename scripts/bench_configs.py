@@ -35,6 +35,10 @@ CASES = {
     "k48d30_eval": (5_000_000, 48, 30, _lib.MODE_GAUSS, ("logq",)),
     "k56d20_eval": (5_000_000, 56, 20, _lib.MODE_GAUSS, ("logq",)),
     "k17d30_eval": (5_000_000, 17, 30, _lib.MODE_GAUSS, ("logq",)),
+    "k20d30_rho": (5_000_000, 20, 30, _lib.MODE_GAUSS, ("logq", "resp")),
+    "k40d20_rho": (5_000_000, 40, 20, _lib.MODE_GAUSS, ("logq", "resp")),
+    "k48d30_rho": (5_000_000, 48, 30, _lib.MODE_GAUSS, ("logq", "resp")),
+    "k100d20_rho": (5_000_000, 100, 20, _lib.MODE_GAUSS, ("logq", "resp")),
 }
 
 

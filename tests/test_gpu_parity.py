@@ -292,7 +292,10 @@ def test_k2_vs_numpy_moments(pm):
     rng = np.random.default_rng(3)
     for (K, D, N, use_g, use_w) in [(1, 1, 5, False, False), (3, 2, 77, True, True), (32, 30, 3001, False, True),
                                     (64, 20, 2500, False, False), (16, 40, 1111, True, True), (5, 47, 400, True, False),
-                                    (130, 6, 999, False, True)]:
+                                    (130, 6, 999, False, True),
+                                    # component-block counts 3, 5, 6, 7 and two chunks of 7 (k2_inst.cu)
+                                    (20, 30, 1500, False, True), (40, 20, 1300, True, True), (48, 30, 1200, False, False),
+                                    (50, 9, 800, True, False), (100, 12, 700, False, True), (21, 3, 300, True, True)]:
         x = rng.normal(size=(N, D)) + 2.0
         rho = rng.uniform(size=(N, K))
         gam = rng.uniform(0.5, 2.0, size=(N, K)) if use_g else None
