@@ -16,10 +16,13 @@
 // sqrt(F) eps |b_k|^2; k1_prepare allows this form only while max_k |b_k|^2 <= kMmaMaxBias2 (error of q below ~1e-11),
 // otherwise k1_fast_eval (|b| <= 1e4) or the exact-difference form run -- all decided on the device, no host sync.
 //
-// Mapping: persistent CTAs (one per SM), 8 warps.  theta for ALL components stays in shared memory for the whole
-// kernel ([feature quad][component][4], 127 KB at K=32, D=30), so there is no ring and no barrier in the sample loop.
-// A warp owns 8 NB samples per tile: it stages x - c (plus the constant column 1 and a zero column) in its private
-// shared-memory slice, then per feature quad loads CB theta fragments, forms NB phi fragments (2 LDS + DMUL each) and
+// Mapping: persistent CTAs (one per SM), NW = 16 warps (four per scheduler: a warp issues at most one DMMA per ~32 clk,
+// the pipe takes one per 16, and a warp in its epilogue issues none).  theta for ALL components of the launch stays in
+// shared memory for the whole kernel ([feature quad][component][4], 127 KB at K=32, D=30), so there is no ring and no
+// barrier in the sample loop; mixtures whose theta does not fit are evaluated in component groups (MmaArgs below).
+// A warp owns 8 NB samples per tile: its private shared-memory slice is filled by cp.async with the rows of the NEXT
+// tile while the epilogue of the current one runs (x - c in place, plus a constant column 1 and a zero column), then
+// per feature quad it loads CB theta fragments, forms NB phi fragments (2 LDS + DMUL each) and
 // issues NB x CB DMMAs into 8x8 (sample x component) accumulators.  A sample's K log-pdfs end up inside one quad of
 // lanes, so the log-sum-exp is two shuffles deep and the N x K outputs leave as 16-byte stores, two full sectors per
 // quad.  The second pass (rho = exp(lp) w_k / (exp(log q) + tiny), or the VB soft-max with its sum r log r) happens
