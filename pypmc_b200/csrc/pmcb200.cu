@@ -79,7 +79,7 @@ using namespace pmc;
 
 // K2: component-block counts 2..8 (true) or powers of two only (false) by default; see pmcb200_suffstats
 #ifndef K2_FINE_BLOCKS_DEFAULT
-#define K2_FINE_BLOCKS_DEFAULT 0
+#define K2_FINE_BLOCKS_DEFAULT 1
 #endif
 
 struct DevBuf {
