@@ -79,6 +79,57 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// Producer step for KP <= 32 CV and DP4 <= 64: PR rows per warp pass, every global load of the pass issued before its
+// first use.  Lane l handles columns l + 32 c of V (c < CV) and of Y (c < 2).
+template <int PR, int CV>
+__device__ __forceinline__ void k2_fill_stage(const StatsArgs& a, double* Vs, double* Ys, const double* shift_s,
+                                              int64_t row0, int rows, int pw, int lane, bool has_g) {
+  const int D = a.d, KP = a.KP, DP4 = a.DP4, TN = a.tn, VS = a.VS, YS = a.YS;
+  for (int rb = pw * PR; rb < TN; rb += 4 * PR) {
+    double w[PR], rv[PR][CV], gv[PR][CV], xv[PR][2];
+#pragma unroll
+    for (int u = 0; u < PR; ++u) {
+      const bool rin = rb + u < rows;
+      const int64_t row = row0 + rb + u;
+      w[u] = (a.sw && rin) ? __ldg(a.sw + row) : 1.0;
+#pragma unroll
+      for (int c = 0; c < CV; ++c) {
+        const int kk = lane + 32 * c;
+        const bool in = rin && kk < a.k;
+        rv[u][c] = in ? __ldg(a.rho + row * a.ld_rho + kk) : 0.0;
+        gv[u][c] = (in && has_g) ? __ldg(a.gamma + row * a.ld_rho + kk) : 1.0;
+      }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int kk = lane + 32 * c;
+        xv[u][c] = (rin && kk < D) ? __ldg(a.x + row * a.ldx + kk) : 0.0;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CV; ++c) {
+      const int kk = lane + 32 * c;                         // column of V handled by this lane
+      if (kk < KP) {
+#pragma unroll
+        for (int u = 0; u < PR; ++u)
+          if (rb + u < TN) Vs[(rb + u) * VS + kk] = rv[u][c] * w[u] * gv[u][c];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int kk = lane + 32 * c;                         // column of Y handled by this lane
+      if (kk < DP4) {
+        const double sh = shift_s[kk];
+#pragma unroll
+        for (int u = 0; u < PR; ++u) {
+          double y = 0.0;
+          if (rb + u < rows) y = (kk < D) ? (xv[u][c] - sh) : ((kk == D) ? 1.0 : 0.0);
+          if (rb + u < TN) Ys[(rb + u) * YS + kk] = y;
+        }
+      }
+    }
+  }
+}
+
 // Stage layout (doubles): V [TN][KP] | Y [TN][DP4].  The producer warpgroup (88 registers) reads rho / gamma /
 // x / w rows from global memory, forms v = w rho gamma and yh = [x - shift, 1, 0...] and stores them; the two
 // consumer warpgroups (208 registers, setmaxnreg) only ever touch shared memory and the FP64 pipe.
@@ -130,41 +181,11 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_suffstats(const StatsArgs a)
       if (KP <= 64 && DP4 <= 64) {
         // common sizes: every global load of a 4-row step is issued before the first use (about 20 in flight per
         // thread), so a step costs one memory latency instead of one per column block
-        for (int rb = pw * K2_PR; rb < TN; rb += 4 * K2_PR) {
-          double w[K2_PR], rv[K2_PR][2], gv[K2_PR][2], xv[K2_PR][2];
-#pragma unroll
-          for (int u = 0; u < K2_PR; ++u) {
-            const bool rin = rb + u < rows;
-            const int64_t row = row0 + rb + u;
-            w[u] = (a.sw && rin) ? __ldg(a.sw + row) : 1.0;
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              const int kk = lane + 32 * c;
-              const bool in = rin && kk < a.k;
-              rv[u][c] = in ? __ldg(a.rho + row * a.ld_rho + kk) : 0.0;
-              gv[u][c] = (in && has_g) ? __ldg(a.gamma + row * a.ld_rho + kk) : 1.0;
-              xv[u][c] = (rin && kk < D) ? __ldg(a.x + row * a.ldx + kk) : 0.0;
-            }
-          }
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const int kk = lane + 32 * c;                         // column of V and of Y handled by this lane
-            if (kk < KP) {
-#pragma unroll
-              for (int u = 0; u < K2_PR; ++u)
-                if (rb + u < TN) Vs[(rb + u) * VS + kk] = rv[u][c] * w[u] * gv[u][c];
-            }
-            if (kk < DP4) {
-              const double sh = shift_s[kk];
-#pragma unroll
-              for (int u = 0; u < K2_PR; ++u) {
-                double y = 0.0;
-                if (rb + u < rows) y = (kk < D) ? (xv[u][c] - sh) : ((kk == D) ? 1.0 : 0.0);
-                if (rb + u < TN) Ys[(rb + u) * YS + kk] = y;
-              }
-            }
-          }
-        }
+        k2_fill_stage<K2_PR, 2>(a, Vs, Ys, shift_s, row0, rows, pw, lane, has_g);
+      } else if (KP <= 128 && DP4 <= 64) {
+        // 65..128 components: the same with two rows in flight and four column blocks per lane (the register budget of
+        // the producer warps, 88, holds 2 x (4 rho + 4 gamma + 2 x) values)
+        k2_fill_stage<2, 4>(a, Vs, Ys, shift_s, row0, rows, pw, lane, has_g);
       } else {
         for (int rb = pw * K2_PR; rb < TN; rb += 4 * K2_PR) {       // K2_PR rows in flight per warp
           double w[K2_PR];

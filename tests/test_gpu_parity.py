@@ -295,7 +295,9 @@ def test_k2_vs_numpy_moments(pm):
                                     (130, 6, 999, False, True),
                                     # component-block counts 3, 5, 6, 7 and two chunks of 7 (k2_inst.cu)
                                     (20, 30, 1500, False, True), (40, 20, 1300, True, True), (48, 30, 1200, False, False),
-                                    (50, 9, 800, True, False), (100, 12, 700, False, True), (21, 3, 300, True, True)]:
+                                    (50, 9, 800, True, False), (100, 12, 700, False, True), (21, 3, 300, True, True),
+                                    # 65..128 components: the producer warps' second load path
+                                    (128, 10, 600, True, True), (96, 33, 500, False, False), (72, 20, 900, True, False)]:
         x = rng.normal(size=(N, D)) + 2.0
         rho = rng.uniform(size=(N, K))
         gam = rng.uniform(0.5, 2.0, size=(N, K)) if use_g else None
