@@ -64,6 +64,8 @@ struct StatsArgs {
   int nFB;              // MMA form: feature blocks of 8 = ceil(F / 8)
   int fchunks;          // MMA form: CTAs (gridDim.y direction) sharing the feature blocks
   int fbw;              // MMA form: feature blocks per warp (= template FB)
+  int chunked;          // MMA form, several CTAs share the component blocks: each stages only its own columns of v
+  int kchunk, cb8;      // ... kchunk columns staged (multiple of 16), first column = (blockIdx.y / fchunks) * cb8
   double* partial;      // [gridDim.x, k, F+2]   (column 0 = A, column 1+f = Out[k,f], column F+1 = sum w rho ln gamma)
 };
 
@@ -83,8 +85,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // first use.  Lane l handles columns l + 32 c of V (c < CV) and of Y (c < 2).
 template <int PR, int CV>
 __device__ __forceinline__ void k2_fill_stage(const StatsArgs& a, double* Vs, double* Ys, const double* shift_s,
-                                              int64_t row0, int rows, int pw, int lane, bool has_g) {
-  const int D = a.d, KP = a.KP, DP4 = a.DP4, TN = a.tn, VS = a.VS, YS = a.YS;
+                                              int64_t row0, int rows, int pw, int lane, bool has_g, int KP,
+                                              const double* __restrict__ rho, const double* __restrict__ gamma, int kvalid) {
+  // rho / gamma point at this CTA's first staged column; kvalid of the KP staged columns hold components
+  const int D = a.d, DP4 = a.DP4, TN = a.tn, VS = a.VS, YS = a.YS;
   for (int rb = pw * PR; rb < TN; rb += 4 * PR) {
     double w[PR], rv[PR][CV], gv[PR][CV], xv[PR][2];
 #pragma unroll
@@ -95,9 +99,9 @@ __device__ __forceinline__ void k2_fill_stage(const StatsArgs& a, double* Vs, do
 #pragma unroll
       for (int c = 0; c < CV; ++c) {
         const int kk = lane + 32 * c;
-        const bool in = rin && kk < a.k;
-        rv[u][c] = in ? __ldg(a.rho + row * a.ld_rho + kk) : 0.0;
-        gv[u][c] = (in && has_g) ? __ldg(a.gamma + row * a.ld_rho + kk) : 1.0;
+        const bool in = rin && kk < kvalid;
+        rv[u][c] = in ? __ldg(rho + row * a.ld_rho + kk) : 0.0;
+        gv[u][c] = (in && has_g) ? __ldg(gamma + row * a.ld_rho + kk) : 1.0;
       }
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -146,6 +150,11 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_suffstats(const StatsArgs a)
   const int tid = threadIdx.x;
   const int D = a.d, KP = a.KP, DP4 = a.DP4, TN = a.tn, VS = a.VS, YS = a.YS;
   const bool has_g = a.gamma != nullptr;
+  // columns of v this CTA stages: all KP, or (several CTAs sharing the component blocks) its own kchunk from koff on
+  const int KW = a.chunked ? a.kchunk : KP, koff = a.chunked ? int(blockIdx.y / a.fchunks) * a.cb8 : 0;
+  const int kvalid = min(KW, a.k - koff);
+  const double* const rho_c = a.rho + koff;
+  const double* const gamma_c = has_g ? a.gamma + koff : nullptr;
   const int stage_len = TN * (VS + YS);
   double* stage0 = reinterpret_cast<double*>(smem_raw);
   double* shift_s = stage0 + K2_STAGES * stage_len;               // [DP4]
@@ -178,26 +187,26 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_suffstats(const StatsArgs a)
       double* Ys = Vs + TN * VS;
       const int64_t row0 = tile * TN;
       const int rows = int((a.n - row0 < TN) ? (a.n - row0) : TN);
-      if (KP <= 64 && DP4 <= 64) {
+      if (KW <= 64 && DP4 <= 64) {
         // common sizes: every global load of a 4-row step is issued before the first use (about 20 in flight per
         // thread), so a step costs one memory latency instead of one per column block
-        k2_fill_stage<K2_PR, 2>(a, Vs, Ys, shift_s, row0, rows, pw, lane, has_g);
-      } else if (KP <= 128 && DP4 <= 64) {
+        k2_fill_stage<K2_PR, 2>(a, Vs, Ys, shift_s, row0, rows, pw, lane, has_g, KW, rho_c, gamma_c, kvalid);
+      } else if (KW <= 128 && DP4 <= 64) {
         // 65..128 components: the same with two rows in flight and four column blocks per lane (the register budget of
         // the producer warps, 88, holds 2 x (4 rho + 4 gamma + 2 x) values)
-        k2_fill_stage<2, 4>(a, Vs, Ys, shift_s, row0, rows, pw, lane, has_g);
+        k2_fill_stage<2, 4>(a, Vs, Ys, shift_s, row0, rows, pw, lane, has_g, KW, rho_c, gamma_c, kvalid);
       } else {
         for (int rb = pw * K2_PR; rb < TN; rb += 4 * K2_PR) {       // K2_PR rows in flight per warp
           double w[K2_PR];
   #pragma unroll
           for (int u = 0; u < K2_PR; ++u) w[u] = (a.sw && rb + u < rows) ? __ldg(a.sw + row0 + rb + u) : 1.0;
-          for (int kk = lane; kk < KP; kk += 32) {
+          for (int kk = lane; kk < KW; kk += 32) {
             double rv[K2_PR], gv[K2_PR];
   #pragma unroll
             for (int u = 0; u < K2_PR; ++u) {
-              const bool in = (rb + u < rows) && (kk < a.k);
-              rv[u] = in ? __ldg(a.rho + (row0 + rb + u) * a.ld_rho + kk) : 0.0;
-              gv[u] = (in && has_g) ? __ldg(a.gamma + (row0 + rb + u) * a.ld_rho + kk) : 1.0;
+              const bool in = (rb + u < rows) && (kk < kvalid);
+              rv[u] = in ? __ldg(rho_c + (row0 + rb + u) * a.ld_rho + kk) : 0.0;
+              gv[u] = (in && has_g) ? __ldg(gamma_c + (row0 + rb + u) * a.ld_rho + kk) : 1.0;
             }
   #pragma unroll
             for (int u = 0; u < K2_PR; ++u)
@@ -251,10 +260,13 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_suffstats(const StatsArgs a)
       }
       off_i[fb] = oi; off_j[fb] = oj;
     }
-    // component blocks beyond KP/8 (cb_total not a multiple of CB) re-read block 0 and are dropped at the end
+    // staged column of each of this warp's component blocks: with `chunked` the CTA staged only its own columns (from
+    // 0), otherwise all of them; blocks beyond KP/8 (cb_total not a multiple of CB) re-read column block 0 and are
+    // dropped at the end
     int cb_off[CB];
 #pragma unroll
-    for (int cb = 0; cb < CB; ++cb) cb_off[cb] = (cb_first + cb < cb_total) ? cb * 8 : -cb_first * 8;
+    for (int cb = 0; cb < CB; ++cb)
+      cb_off[cb] = (cb_first + cb < cb_total) ? (a.chunked ? 0 : cb_first * 8) + cb * 8 : 0;
     double acc[CB][FB][2];
 #pragma unroll
     for (int cb = 0; cb < CB; ++cb)
@@ -272,7 +284,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_suffstats(const StatsArgs a)
         // load of a step can be issued before its first DMMA and the 32 DMMAs go back to back
 #pragma unroll 2
         for (int n0 = 0; n0 < TN; n0 += 4) {
-          const double* vrow = Vs + (n0 + tq) * VS + cb_first * 8 + g;
+          const double* vrow = Vs + (n0 + tq) * VS + g;
           const double* yrow = Ys + (n0 + tq) * YS;
           double av[CB], bv[FB];
 #pragma unroll

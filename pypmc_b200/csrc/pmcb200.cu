@@ -439,12 +439,16 @@ int pmcb200_suffstats(pmcb200_ctx* c, const double* x, int64_t n, int64_t ldx, i
     a.fbw = fbw;
     gy = a.fchunks * cchunks;
     a.DP4 = ((d + 2 + 3) / 4) * 4;                       // [y, 1, 0...]: always at least one zero column (index d+1)
-    a.VS = a.KP + 4;                                     // row strides = 4 (mod 16) doubles: the 8 x 4 fragment loads of a
+    a.chunked = (cchunks > 1) ? 1 : 0;                   // several CTAs share the component blocks: each stages its own
+    a.cb8 = cbw * 8;
+    a.kchunk = ((a.cb8 + 15) / 16) * 16;
+    a.VS = (a.chunked ? a.kchunk : a.KP) + 4;            // row strides = 4 (mod 16) doubles: the 8 x 4 fragment loads of a
     a.YS = ((a.DP4 + 11) / 16) * 16 + 4;                 // half-warp then touch 16 different 8-byte banks
   } else {
     a.nFB = 0;
     a.fchunks = 1;
     a.fbw = 0;
+    a.chunked = 0; a.cb8 = 0; a.kchunk = 0;
     gy = (a.LT + K2_CONSUMERS - 1) / K2_CONSUMERS;       // lane tiles -> CTAs of 8 consumer warps
     a.DP4 = a.Lq * 4;
     a.VS = a.KP;
