@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PMCB200_VERSION 100
+#define PMCB200_VERSION 101
 
 #define PMCB200_MODE_GAUSS 0     /* Gauss components      density/gauss.pyx:132-153      */
 #define PMCB200_MODE_STUDENT_T 1 /* StudentT components   density/student_t.pyx:135-166  */
@@ -155,6 +155,12 @@ int pmcb200_mixture_propose(pmcb200_ctx* ctx, int64_t n, int d, int k,
  * 2 = DFMA + one broadcast LDS.128 per 2 DFMA, 3 = FP64 mma.sync m8n8k4 (DMMA).
  */
 int pmcb200_fp64_peak(pmcb200_ctx* ctx, int which, int iters, double* gflops_out, double* ms_out);
+
+/* Name of the K1 kernel that did the work in the last pmcb200_mixture_eval call on this context, e.g.
+ * "k1_mma_eval<4, 2, 16, false>", "k1_fast_eval<30>" or "k1_mixture_eval<30>" -- the three forms are chosen on the
+ * device (k1_prepare / k1_mma_prepare), so this reads the decision flags back (synchronises the device).  Writes a
+ * NUL-terminated string of at most len - 1 characters; for bench.py's roofline record. */
+int pmcb200_last_k1_kernel(pmcb200_ctx* ctx, char* buf, int len);
 
 /* kernels launched by this library since the context was created (for bench.py's gpu_launches) */
 int64_t pmcb200_launch_count(pmcb200_ctx* ctx);

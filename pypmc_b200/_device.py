@@ -68,8 +68,9 @@ def to_device(a, device=None, dtype=None):
     return t.from_numpy(arr).to(dev)
 
 
-def current_stream_ptr() -> int:
-    return torch().cuda.current_stream().cuda_stream
+def current_stream_ptr(device=None) -> int:
+    """cudaStream_t of torch's current stream on ``device`` (default: this process's device)."""
+    return torch().cuda.current_stream(_lib.default_device() if device is None else device).cuda_stream
 
 
 class PackedComponents:
@@ -82,9 +83,10 @@ class PackedComponents:
         if weights is not None:
             # mixture weights live in scalar slot S_WEIGHT (last 8 doubles of a record)
             self.records[:, self.records.shape[1] - _lib.NUM_SCALARS + _lib.S_WEIGHT] = weights
-        self._dev = None
+        self._dev = {}
 
-    def device(self):
-        if self._dev is None:
-            self._dev = (to_device(self.records), to_device(self.cols))
-        return self._dev
+    def device(self, index=None):
+        index = _lib.default_device() if index is None else index
+        if index not in self._dev:
+            self._dev[index] = (to_device(self.records, index), to_device(self.cols, index))
+        return self._dev[index]

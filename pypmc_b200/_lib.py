@@ -47,6 +47,7 @@ SIGNATURES = {
         _vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_uint64, ctypes.c_uint64, _vp,
         ctypes.c_int64, _vp, _vp]),
     "pmcb200_fp64_peak": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _c_double_p, _c_double_p]),
+    "pmcb200_last_k1_kernel": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_int]),
     "pmcb200_launch_count": (ctypes.c_int64, [_vp]),
 }
 
@@ -68,7 +69,7 @@ def load():
             fn = getattr(lib, name)  # AttributeError if the symbol is missing: fail loudly
             fn.restype = res
             fn.argtypes = args
-        if lib.pmcb200_version() < 100:
+        if lib.pmcb200_version() < 101:
             raise ImportError("libpmcb200.so is stale; rebuild with python -m pypmc_b200._build --force")
         _lib = lib
         return lib
@@ -169,6 +170,12 @@ class Context:
         g, ms = ctypes.c_double(), ctypes.c_double()
         _check(load().pmcb200_fp64_peak(self.handle, which, iters, ctypes.byref(g), ctypes.byref(ms)), "pmcb200_fp64_peak")
         return g.value, ms.value
+
+    def last_k1_kernel(self) -> str:
+        """Name of the K1 kernel that did the work in the last ``mixture_eval`` on this context (reads the device flags)."""
+        buf = ctypes.create_string_buffer(128)
+        _check(load().pmcb200_last_k1_kernel(self.handle, buf, 128), "pmcb200_last_k1_kernel")
+        return buf.value.decode()
 
     def launch_count(self) -> int:
         return int(load().pmcb200_launch_count(self.handle))

@@ -20,7 +20,7 @@ struct K1Launch {
     int k0[kMaxGroups] = {}, count[kMaxGroups] = {}, cb[kMaxGroups] = {};   // first component, components, blocks of 8
     size_t theta_off[kMaxGroups] = {};    // offset (doubles) of the group's theta [steps][8 cb][4]
     size_t theta_len = 0;
-    int steps = 0, ys = 0;
+    int steps = 0;
   } mma;
   const double* theta = nullptr;
 };
@@ -29,6 +29,7 @@ struct K1Launch {
 // does not apply (too few components, tiny D, or a grouping that would pad the component count by more than 20 %).
 bool k1_mma_plan(int kl, int d, K1Launch::MmaPlan* plan);
 int k1_mma_launch(const K1Launch& l, int sm_count, cudaStream_t stream);
+int k1_mma_nb(int cb, bool second);   // sample blocks per warp of the instantiation k1_mma_launch picks
 
 // returns cudaError_t as int; grid <= #SMs (persistent CTAs, one per SM)
 template <int DP>

@@ -15,8 +15,13 @@ constexpr size_t kSmemLimit = 227 * 1024;
 // for the eval-only instantiation (theta fragments then feed two DMMAs each: K=56, D=20 4.63 vs 4.99 ms), up to CB = 5
 // with the fused second pass, whose second register array would spill beyond that (C3 VB 17.8 vs 13.7 ms).  The
 // per-sample arithmetic does not depend on NB, so both instantiations give the same log q bit for bit.
-static int nb_for(int cb, bool second) { return (cb <= 5 || !second) ? 2 : 1; }
+static int nb_for(int cb, bool second) {
+  static const char* env = getenv("PMCB200_K1_NB1");              // tuning runs: one sample block for the fused second pass from CB = N on
+  const int from = env ? atoi(env) : 6;
+  return (second && cb >= 5 && cb >= from) ? 1 : 2;
+}
 constexpr int kWarps = 16;
+int k1_mma_nb(int cb, bool second) { return nb_for(cb, second); }
 
 bool k1_mma_plan(int kl, int d, K1Launch::MmaPlan* plan) {
   if (kl < 9 || d < 8) return false;                  // few components / tiny D: the DFMA form's epilogue-bound regime
@@ -33,7 +38,6 @@ bool k1_mma_plan(int kl, int d, K1Launch::MmaPlan* plan) {
   if (groups > 1 && cbmax < 4 && d < 33) return false;
   plan->groups = groups;
   plan->steps = (k1m_features(d) + 3) / 4;
-  plan->ys = k1m_row_stride(d);
   size_t off = 0;
   for (int g = 0; g < groups; ++g) {
     plan->k0[g] = g * 8 * cbmax;
@@ -46,19 +50,19 @@ bool k1_mma_plan(int kl, int d, K1Launch::MmaPlan* plan) {
   return true;
 }
 
-template <int CB, int NB, int NW, bool SECOND>
+template <int CB, int NB, int NW, bool SECOND, int DIAG = 0>
 static int launch(const MmaArgs& ma, int sm_count, size_t smem, cudaStream_t stream) {
   static PerDeviceFlag attr_flag;
   bool& attr_set = attr_flag.here();
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k1_mma_eval<CB, NB, NW, SECOND>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemLimit));
+    cudaError_t e = cudaFuncSetAttribute(k1_mma_eval<CB, NB, NW, SECOND, DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemLimit));
     if (e != cudaSuccess) return int(e);
     attr_set = true;
   }
   const int ts = 8 * NB * NW;
   const int64_t tiles = (ma.e.n + ts - 1) / ts;
   const int grid = int(std::min<int64_t>(tiles, sm_count));
-  k1_mma_eval<CB, NB, NW, SECOND><<<grid, NW * 32, smem, stream>>>(ma);
+  k1_mma_eval<CB, NB, NW, SECOND, DIAG><<<grid, NW * 32, smem, stream>>>(ma);
   return int(cudaGetLastError());
 }
 
@@ -69,19 +73,35 @@ int k1_mma_launch(const K1Launch& l, int sm_count, cudaStream_t stream) {
   const int rl = record_len((l.base.d + 1) & ~1);
   for (int g = 0; g < p.groups; ++g) {
     const int cb = p.cb[g], nb = nb_for(cb, second);
-    MmaArgs ma{l.base, l.theta + p.theta_off[g], l.shift, l.flag, p.steps, 8 * cb, p.ys, g, p.groups, l.rowstat};
+    MmaArgs ma{l.base, l.theta + p.theta_off[g], l.shift, l.flag, p.steps, 8 * cb, g, p.groups, l.rowstat};
     ma.e.records = l.derived + size_t(p.k0[g]) * rl;
     ma.e.cols = l.base.cols + p.k0[g];
     ma.e.kl = p.count[g];
     if (g + 1 < p.groups) ma.e.partials = nullptr;                   // the sums belong to the last launch
     const size_t smem = k1m_smem_bytes(l.base.d, 8 * cb, nb, kWarps);
     int rc = int(cudaErrorInvalidValue);
-#define PMC_K1M_CASE(CBV, NB_EVAL, NB_SECOND)                                                   \
+    // measurement builds: PMCB200_K1_DIAG=1..7 swaps in a kernel with parts removed (WRONG RESULTS; timing only)
+    const char* diag_env = getenv("PMCB200_K1_DIAG");
+    const int diag = diag_env ? atoi(diag_env) : 0;
+    if (diag && cb == 4 && !second) {
+      switch (diag) {
+        case 1: rc = launch<4, 2, kWarps, false, 1>(ma, sm_count, smem, stream); break;
+        case 2: rc = launch<4, 2, kWarps, false, 2>(ma, sm_count, smem, stream); break;
+        case 3: rc = launch<4, 2, kWarps, false, 3>(ma, sm_count, smem, stream); break;
+        case 4: rc = launch<4, 2, kWarps, false, 4>(ma, sm_count, smem, stream); break;
+        case 6: rc = launch<4, 2, kWarps, false, 6>(ma, sm_count, smem, stream); break;
+        default: break;
+      }
+      if (rc != 0) return rc;
+      continue;
+    }
+#define PMC_K1M_CASE(CBV, NB_ALT)                                                              \
     if (cb == CBV)                                                                              \
-      rc = second ? launch<CBV, NB_SECOND, kWarps, true>(ma, sm_count, smem, stream)            \
-                  : launch<CBV, NB_EVAL, kWarps, false>(ma, sm_count, smem, stream);
-    PMC_K1M_CASE(2, 2, 2) PMC_K1M_CASE(3, 2, 2) PMC_K1M_CASE(4, 2, 2) PMC_K1M_CASE(5, 2, 2) PMC_K1M_CASE(6, 2, 1)
-    PMC_K1M_CASE(7, 2, 1) PMC_K1M_CASE(8, 2, 1)
+      rc = !second ? launch<CBV, 2, kWarps, false>(ma, sm_count, smem, stream)                  \
+           : (nb == 2) ? launch<CBV, 2, kWarps, true>(ma, sm_count, smem, stream)               \
+                       : launch<CBV, NB_ALT, kWarps, true>(ma, sm_count, smem, stream);
+    PMC_K1M_CASE(2, 2) PMC_K1M_CASE(3, 2) PMC_K1M_CASE(4, 2) PMC_K1M_CASE(5, 1) PMC_K1M_CASE(6, 1)
+    PMC_K1M_CASE(7, 1) PMC_K1M_CASE(8, 1)
 #undef PMC_K1M_CASE
     if (rc != 0) return rc;
   }

@@ -12,29 +12,42 @@
 //     theta_k  = [ |b_k|^2 | -2 (T_k^T b_k)_i | M_ii, 2 M_ij ]     b_k = T_k d_k       (k1_mma_prepare)
 // i.e. a dense (N x F).(F x K) product with F (D(D+1)/2 + D + 1) FMAs per pair -- the algorithmic count, nothing
 // padded but the last feature quad -- whose left operand is formed on the fly (one DMUL per fragment).
-// Rounding: the terms are of size |b_k|^2 where the result may be small, so the absolute error of q is about
-// sqrt(F) eps |b_k|^2; k1_prepare allows this form only while max_k |b_k|^2 <= kMmaMaxBias2 (error of q below ~1e-11),
-// otherwise k1_fast_eval (|b| <= 1e4) or the exact-difference form run -- all decided on the device, no host sync.
+// Rounding: the expanded terms cancel, so the absolute error of q is about sqrt(F) eps A_k with A_k = sum_f
+// |theta_kf| |phi_f(d_k)|, the size of the terms at the component's own centre (= |b_k|^2 for a well-conditioned
+// component, up to kappa times more when d_k lies along a wide axis of an ill-conditioned covariance).
+// k1_mma_prepare admits this form only while max_k s_k A_k <= kMmaMaxBias2 (s_k = the factor q carries in the
+// exponent; error of the log-pdf below ~3e-11), otherwise k1_fast_eval (|b| <= 1e4) or the exact-difference form run
+// -- all decided on the device, no host sync.
 //
 // Mapping: persistent CTAs (one per SM), NW = 16 warps (four per scheduler: a warp issues at most one DMMA per ~32 clk,
 // the pipe takes one per 16, and a warp in its epilogue issues none).  theta for ALL components of the launch stays in
 // shared memory for the whole kernel ([feature quad][component][4], 127 KB at K=32, D=30), so there is no ring and no
 // barrier in the sample loop; mixtures whose theta does not fit are evaluated in component groups (MmaArgs below).
-// A warp owns 8 NB samples per tile: its private shared-memory slice is filled by cp.async with the rows of the NEXT
-// tile while the epilogue of the current one runs (x - c in place, plus a constant column 1 and a zero column), then
-// per feature quad it loads CB theta fragments, forms NB phi fragments (2 LDS + DMUL each) and
-// issues NB x CB DMMAs into 8x8 (sample x component) accumulators.  A sample's K log-pdfs end up inside one quad of
-// lanes, so the log-sum-exp is two shuffles deep and the N x K outputs leave as 16-byte stores, two full sectors per
-// quad.  The second pass (rho = exp(lp) w_k / (exp(log q) + tiny), or the VB soft-max with its sum r log r) happens
-// here too, on the log-pdfs still in registers -- k1_finish, the streaming pass behind the DFMA forms, returns at once.
+// A warp owns 8 NB samples per tile.  Its private slice holds them TRANSPOSED, [column][sample slot], the two sample
+// blocks of a lane interleaved (slot 2g + nb): the x_i operand of a feature quad is then ONE 128-byte wavefront and one
+// LDS.128 per lane serves both sample blocks (the row-major slice of round 1 took 2 LDS.64 and 4 wavefronts for it;
+// bare loop 86.9 -> 90.6 % of the DMMA peak, profiles/r02b_dmma_feed.md).  The slice is filled by cp.async with the
+// rows of the NEXT tile while the epilogue of the current one runs; x - c is applied in place.  Per feature quad: one
+// table word (byte offsets of the quad's two columns), 2 LDS.128 + NB DMUL for phi, CB LDS.64 for theta, NB x CB
+// DMMAs into 8x8 (sample x component) accumulators; the operands of quad s+1 are fetched before the DMMAs of quad s.
+// A sample's K log-pdfs end up inside one quad of lanes, so the log-sum-exp is two shuffles deep and the N x K
+// outputs leave as 16-byte stores, two full sectors per quad.  The second pass (rho = exp(lp) w_k / (exp(log q) +
+// tiny), or the VB soft-max with its sum r log r) happens here too, on the log-pdfs still in registers, one sample
+// block at a time (no spills) -- k1_finish, the streaming pass behind the DFMA forms, returns at once.
+// The exponentials of the log-sum-exp (one per pair: 5 % of the FP64 pipe's time with the library exp,
+// profiles/r02b_k1_diag.md) use a 256-entry table of 2^(j/256) and a degree-4 polynomial -- 9 FP64 instructions
+// instead of 17, <= 1 ulp; arguments below -707, where the result leaves the normal range, are redone with the
+// library function so that the deep tails keep the reference's subnormal arithmetic.
 #pragma once
 
+#include "k1_exp_table.cuh"
 #include "k1_fast_eval.cuh"
 
 namespace pmc {
 
-constexpr double kMmaMaxBias2 = 2.0e4;   // above this |b_k|^2 the DFMA forms run instead
-constexpr int K1M_SCAL = 8;              // scalars per component kept in shared memory
+constexpr double kMmaMaxBias2 = 8.0e4;   // above this size of the cancelling terms (A_k >= 4 |b_k|^2) the DFMA forms run instead
+constexpr int K1M_SCAL = 6;              // scalars per component kept in shared memory (S0..S4, weight), [scalar][KP]
+constexpr int K1M_EXPTAB = 256;          // entries of the 2^(j/256) table
 
 struct MmaArgs {
   EvalArgs e;             // e.records = derived records ([T | -b | scalars]); only the scalars are read here
@@ -43,7 +56,6 @@ struct MmaArgs {
   const int* flag;        // flag[0] != 0: exact-difference form runs; else flag[1] != 0: this form runs; else k1_fast_eval
   int steps;              // feature quads = ceil(F / 4)
   int KP;                 // components (of this group) padded to 8 CB
-  int YS;                 // row stride (doubles) of the staged samples: >= d + 2 and == 4 (mod 16)
   // Component groups: when theta of all components does not fit shared memory, the components are evaluated in
   // `ngroups` launches of at most KP each (e.records / e.cols / e.kl / theta describe THIS group).  The running
   // (max, weighted sum) of the log-sum-exp travels between the launches in rowstat; the last launch finishes log q
@@ -53,10 +65,13 @@ struct MmaArgs {
 };
 
 __host__ __device__ inline int k1m_features(int d) { return 1 + d + d * (d + 1) / 2; }
-__host__ __device__ inline int k1m_row_stride(int d) { return ((d + 2 - 4 + 15) / 16) * 16 + 4; }
+// slots per column of a warp's slice: 8 NB samples + 4 of padding.  The column stride is then 20 (NB = 2) or 12
+// (NB = 1) doubles, == 4 and 12 (mod 16): the x_j loads of a quad -- 4 columns x 8 NB samples -- touch every bank once.
+__host__ __device__ constexpr int k1m_col_stride(int NB) { return 8 * NB + 4; }
 inline size_t k1m_smem_bytes(int d, int KP, int NB, int NW) {
-  const int steps = (k1m_features(d) + 3) / 4, YS = k1m_row_stride(d);
-  return sizeof(double) * (size_t(steps) * KP * 4 + size_t(KP) * K1M_SCAL + YS + size_t(NW) * 8 * NB * YS) +
+  const int steps = (k1m_features(d) + 3) / 4, dp = (d + 1) & ~1;
+  return sizeof(double) * (size_t(steps) * KP * 4 + size_t(KP) * K1M_SCAL + dp + K1M_EXPTAB +
+                           size_t(NW) * (d + 2) * k1m_col_stride(NB)) +
          sizeof(int) * size_t(steps) * 4 + 16;
 }
 
@@ -68,49 +83,88 @@ __device__ __forceinline__ void tri_index(int t, int& r, int& c) {
   c = t - r * (r + 1) / 2;
 }
 
+// exp(x) for -707 <= x <= 0 (the caller diverts anything else): x = (256 m + j) ln2/256 + r, |r| <= ln2/512,
+// exp(x) = 2^m T[j] e^r, e^r - 1 = r + r^2 (1/2 + r/6 + r^2/24) (truncation 4e-17).  9 FP64 instructions; the scaling
+// by 2^m is an integer add on the exponent field (the result stays normal for x >= -707).  Measured against 60-digit
+// arithmetic on 2e4 arguments: <= 2.2e-16 relative.
+__device__ __forceinline__ double exp_tab(double x, const double* __restrict__ tab) {
+  const double magic = 6755399441055744.0;                         // 1.5 * 2^52: the low word of the sum is round(x 256/ln2)
+  const double t = fma(x, 0x1.71547652b82fep+8, magic);            // 256 / ln 2
+  const int k = __double2loint(t);
+  const double kf = t - magic;
+  double r = fma(kf, -0x1.62e42fef80000p-9, x);                    // ln2/256, upper 34 bits: kf * hi is exact
+  r = fma(kf, -0x1.1cf79abc9e3b4p-44, r);                          // ln2/256, remainder
+  const double r2 = r * r;
+  double u = fma(r, 4.16666666666666644e-02, 1.66666666666666657e-01);
+  u = fma(r, u, 0.5);
+  const double p = fma(r2, u, r);
+  const double tj = tab[k & (K1M_EXPTAB - 1)];
+  const double v = fma(tj, p, tj);
+  return __hiloint2double(__double2hiint(v) + (k >> 8) * 1048576, __double2loint(v));
+}
+// Order-preserving 32-bit key of a double's high word (signed compare of keys == compare of the doubles' upper 32 bits)
+// and its inverse (low word zero).  The log-sum-exp only needs A reference point near the largest log-pdf -- any m gives
+// m + log sum_k w_k exp(lp_k - m) -- so the maximum is taken over these keys with integer instructions (the FP64 pipe
+// is the one every warp is waiting for) and m is the decoded key: within 2^-20 relative of the true maximum.
+__device__ __forceinline__ int dkey(double v) {
+  const int hi = __double2hiint(v);
+  return hi ^ ((hi >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ double dkey_value(int key) { return __hiloint2double(key ^ ((key >> 31) & 0x7fffffff), 0); }
+// max(v, 0) on the integer pipe (like fmax: a NaN with the sign bit set also becomes 0)
+__device__ __forceinline__ double clamp0(double v) { return (__double2hiint(v) < 0) ? 0.0 : v; }
+
+constexpr unsigned kExpSlowHi = 0xC0861800u;                        // high word of -707.0: from there on the library exp runs
+
 // ---------------------------------------------------------------------------------------------
 // k1_mma_eval<CB, NB, NW, SECOND>: CB blocks of 8 components (KP = 8 CB), NB blocks of 8 samples per warp and tile,
 // NW warps per CTA; SECOND: the launch also wants rho / r (the eval-only instantiation keeps no exponentials).
+// DIAG (measurement builds only, PMCB200_K1_DIAG): 1 = exponentials replaced by one DFMA, 2 = no sample staging
+// (the slice keeps its first tile), 4 = no epilogue beyond one store per sample -- to attribute the idle pipe time.
 // ---------------------------------------------------------------------------------------------
-template <int CB, int NB, int NW, bool SECOND>
+template <int CB, int NB, int NW, bool SECOND, int DIAG = 0>
 __global__ void __launch_bounds__(NW * 32, 1) k1_mma_eval(const MmaArgs ma) {
+  static_assert(NB == 1 || NB == 2, "one LDS.64 / LDS.128 per operand serves the sample blocks of a lane");
   const EvalArgs& a = ma.e;
   if (ma.flag[0] != 0 || ma.flag[1] == 0) return;
-  constexpr int RW = 8 * NB, TS = RW * NW, KP = 8 * CB;
+  constexpr int RW = 8 * NB, TS = RW * NW, KP = 8 * CB, RS = k1m_col_stride(NB);
   constexpr int UNR = (CB * NB <= 4) ? 4 : (CB * NB >= 12) ? 1 : 2;   // feature quads per loop body (about 16 DMMAs)
-  const int D = a.d, YS = ma.YS, steps = ma.steps;
+  const int D = a.d, steps = ma.steps, dp = (D + 1) & ~1;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double* theta_s = reinterpret_cast<double*>(smem_raw);               // [steps][KP][4]
-  double* scal_s = theta_s + size_t(steps) * KP * 4;                   // [KP][8]
-  double* cs = scal_s + KP * K1M_SCAL;                                 // [YS] shift
-  double* y_all = cs + YS;                                             // [NW][RW][YS]
-  int* tab = reinterpret_cast<int*>(y_all + size_t(NW) * RW * YS); // [steps * 4] (off_i | off_j << 8)
+  double* scal_s = theta_s + size_t(steps) * KP * 4;                   // [K1M_SCAL][KP]
+  double* cs = scal_s + KP * K1M_SCAL;                                 // [dp] shift
+  double* etab = cs + dp;                                              // [256] 2^(j/256)
+  double* y_all = etab + K1M_EXPTAB;                                   // [NW][D + 2][RS]
+  const int slice = (D + 2) * RS;
+  int* tab = reinterpret_cast<int*>(y_all + size_t(NW) * slice);      // [steps * 4] byte offsets (column i | column j << 16)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, tq = lane & 3;
 
-  // ---- prologue: theta, scalars, shift, feature table, constant columns ----
+  // ---- prologue: theta, scalars, shift, exp table, feature table, constant columns ----
   {
     const int n2 = steps * KP * 2;
     const double2* src = reinterpret_cast<const double2*>(ma.theta);
     double2* dst = reinterpret_cast<double2*>(theta_s);
     for (int i = tid; i < n2; i += blockDim.x) dst[i] = __ldg(src + i);
-    const int dp = (D + 1) & ~1, rl = record_len(dp), so = tri_len(dp) + dp;
+    const int rl = record_len(dp), so = tri_len(dp) + dp;
     for (int i = tid; i < KP * K1M_SCAL; i += blockDim.x) {
-      const int k = i / K1M_SCAL, s = i - k * K1M_SCAL;
+      const int s = i / KP, k = i - s * KP;
       scal_s[i] = (k < a.kl) ? a.records[size_t(k) * rl + so + s] : 0.0;
     }
-    for (int j = tid; j < YS; j += blockDim.x) cs[j] = (j < D) ? ma.shift[j] : 0.0;
+    for (int j = tid; j < dp; j += blockDim.x) cs[j] = (j < D) ? ma.shift[j] : 0.0;
+    for (int j = tid; j < K1M_EXPTAB; j += blockDim.x) etab[j] = kExp2Table[j];
     const int F = k1m_features(D);
     for (int f = tid; f < steps * 4; f += blockDim.x) {
       int oi = D + 1, oj = D + 1;                                       // zero column
       if (f == 0) { oi = D; oj = D; }
       else if (f <= D) { oi = f - 1; oj = D; }
       else if (f < F) tri_index(f - 1 - D, oi, oj);
-      tab[f] = oi | (oj << 8);
+      tab[f] = (oi * RS * 8) | ((oj * RS * 8) << 16);
     }
-    for (int i = tid; i < NW * RW * YS; i += blockDim.x) y_all[i] = ((i % YS) == D) ? 1.0 : 0.0;
+    for (int i = tid; i < NW * slice; i += blockDim.x) y_all[i] = ((i % slice) / RS == D) ? 1.0 : 0.0;
   }
   // contiguous output columns (the usual case) allow 16-byte stores
   const bool staged = a.lp_out != nullptr || a.resp_out != nullptr || a.aux_out != nullptr;
@@ -126,35 +180,51 @@ __global__ void __launch_bounds__(NW * 32, 1) k1_mma_eval(const MmaArgs ma) {
   const bool contig = __syncthreads_and(contig_l) != 0;               // also publishes the prologue's stores
   const int col0 = staged ? __ldg(a.cols) : 0;
 
-  double* yw = y_all + size_t(warp) * RW * YS;
-  const double* yg = yw + g * YS;                                      // rows g + 8 nb
+  double* yw = y_all + size_t(warp) * slice;
+  const char* ylane = reinterpret_cast<const char*>(yw + g * NB);      // this lane's sample slot(s) in column 0
   const double* thl = theta_s + g * 4 + tq;                            // theta[s][8 cb + g][tq]
   const int* tabl = tab + tq;
+  const double* scl = scal_s + 2 * tq;                                 // scalars of components 8 cb + 2 tq + {0, 1}
 
   const int64_t num_tiles = (a.n + TS - 1) / TS;
   double part_a = 0.0, part_w = 0.0;
+  unsigned wmask = 0u;                                                 // bit 2 cb + e: component 8 cb + 2 tq + e has a nonzero weight
+#pragma unroll
+  for (int cb = 0; cb < CB; ++cb) {
+    const double2 w2 = *reinterpret_cast<const double2*>(scl + S_WEIGHT * KP + 8 * cb);
+    wmask |= (w2.x != 0.0 ? 1u : 0u) << (2 * cb);
+    wmask |= (w2.y != 0.0 ? 2u : 0u) << (2 * cb);
+  }
 
-  // this warp's rows of a tile -> its shared-memory slice, asynchronously (LDGSTS, lane = column); rows beyond n
-  // are zero-filled.  The shift is applied in place when the tile is picked up.
+  // this warp's rows of a tile -> its slice, asynchronously (LDGSTS, lane = column; sample r -> slot NB (r % 8) + r / 8);
+  // rows beyond n are zero-filled.  The shift is applied in place when the tile is picked up.
   auto stage_rows = [&](int64_t r0) {
+    const bool full = r0 + RW <= a.n;
     for (int j = lane; j < D; j += 32) {
-      const uint32_t dst = smem_u32(yw + j);
-#pragma unroll 8
-      for (int r = 0; r < RW; ++r) {
-        const int64_t row = r0 + r;
-        const bool in = row < a.n;
-        const double* src = in ? (a.x + row * a.ldx + j) : a.x;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + uint32_t(r * YS) * 8u), "l"(src),
-                     "r"(in ? 8 : 0)
-                     : "memory");
+      const uint32_t dst = smem_u32(yw + j * RS);
+      const double* src = a.x + r0 * a.ldx + j;
+      if (full) {
+#pragma unroll
+        for (int r = 0; r < RW; ++r)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + uint32_t(NB * (r & 7) + (r >> 3)) * 8u),
+                       "l"(src + r * a.ldx)
+                       : "memory");
+      } else {
+#pragma unroll
+        for (int r = 0; r < RW; ++r) {
+          const bool in = r0 + r < a.n;
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + uint32_t(NB * (r & 7) + (r >> 3)) * 8u),
+                       "l"(in ? src + r * a.ldx : a.x), "r"(in ? 8 : 0)
+                       : "memory");
+        }
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   if (int64_t(blockIdx.x) < num_tiles) stage_rows(int64_t(blockIdx.x) * TS + int64_t(warp) * RW);
-  // The two warps of a scheduler would run in lock step: both in the DMMA loop (sharing the pipe), then both in the
-  // latency-bound epilogue (pipe idle, 18 % of the time in the first profile).  Starting the second warp one
-  // DMMA-loop later keeps them in opposite phases for the whole kernel: one warp's epilogue hides behind the other's loop.
+  // The warps of a scheduler would run in lock step: all in the DMMA loop (sharing the pipe), then all in the
+  // latency-bound epilogue (pipe idle, 18 % of the time in the first profile).  Starting warp group j that many
+  // DMMA-loops later keeps them in different phases for the whole kernel: a warp's epilogue hides behind the others' loops.
   if (warp >= 4 && num_tiles >= 4 * int64_t(gridDim.x)) {
     const long long t0 = clock64(), wait = (long long)steps * (NB * CB * 16) * (warp / 4);
     while (clock64() - t0 < wait) {
@@ -163,12 +233,20 @@ __global__ void __launch_bounds__(NW * 32, 1) k1_mma_eval(const MmaArgs ma) {
 
   for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const int64_t row0 = tile * TS + int64_t(warp) * RW;
-    // ---- pick up the staged rows: y = x - c in place (each lane owns the columns it copied) ----
+    // ---- pick up the staged rows: y = x - c in place, 16 bytes (two sample slots of one column) per lane and step ----
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    for (int j = lane; j < D; j += 32) {
-      const double c = cs[j];
-#pragma unroll 8
-      for (int r = 0; r < RW; ++r) yw[r * YS + j] -= c;
+    __syncwarp();
+    if (!(DIAG & 2) || tile == blockIdx.x) {
+      constexpr int PPC = RW / 2;                                       // slot pairs per column
+      for (int e2 = lane; e2 < D * PPC; e2 += 32) {
+        const int col = e2 / PPC, pp = e2 - col * PPC;
+        double2* p = reinterpret_cast<double2*>(yw + col * RS + 2 * pp);
+        const double c = cs[col];
+        double2 v = *p;
+        v.x -= c;
+        v.y -= c;
+        *p = v;
+      }
     }
     __syncwarp();
 
@@ -181,13 +259,19 @@ __global__ void __launch_bounds__(NW * 32, 1) k1_mma_eval(const MmaArgs ma) {
     // ---- q = phi . theta over the feature quads; the operands of quad s + 1 are fetched before the DMMAs of quad s ----
     double th_n[CB], yi_n[NB], yj_n[NB];
     auto fetch = [&](int s) {
-      const int t = tabl[4 * s];
-      const double* yi = yg + (t & 0xff);
-      const double* yj = yg + (t >> 8);
+      const unsigned t = unsigned(tabl[4 * s]);
+      const char* pi = ylane + (t & 0xffffu);
+      const char* pj = ylane + (t >> 16);
 #pragma unroll
       for (int cb = 0; cb < CB; ++cb) th_n[cb] = thl[(s * KP + cb * 8) * 4];
-#pragma unroll
-      for (int nb = 0; nb < NB; ++nb) { yi_n[nb] = yi[nb * 8 * YS]; yj_n[nb] = yj[nb * 8 * YS]; }
+      if constexpr (NB == 2) {
+        const double2 vi = *reinterpret_cast<const double2*>(pi), vj = *reinterpret_cast<const double2*>(pj);
+        yi_n[0] = vi.x; yi_n[NB - 1] = vi.y;
+        yj_n[0] = vj.x; yj_n[NB - 1] = vj.y;
+      } else {
+        yi_n[0] = *reinterpret_cast<const double*>(pi);
+        yj_n[0] = *reinterpret_cast<const double*>(pj);
+      }
     };
     fetch(0);
 #pragma unroll UNR
@@ -208,182 +292,249 @@ __global__ void __launch_bounds__(NW * 32, 1) k1_mma_eval(const MmaArgs ma) {
     }
     // ---- the slice is free: start copying this warp's rows of the CTA's next tile behind the epilogue ----
     __syncwarp();
-    if (tile + gridDim.x < num_tiles) stage_rows(row0 + int64_t(gridDim.x) * TS);
+    if (!(DIAG & 2) && tile + gridDim.x < num_tiles) stage_rows(row0 + int64_t(gridDim.x) * TS);
+    if constexpr ((DIAG & 4) != 0) {
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        double t = 0.0;
+#pragma unroll
+        for (int cb = 0; cb < CB; ++cb) t += acc[nb][cb][0] + acc[nb][cb][1];
+        const int64_t row = row0 + 8 * nb + g;
+        if (row < a.n && tq == 0 && a.logq) a.logq[row] = t;
+      }
+      continue;
+    }
 
     // ---- epilogue: lane holds q[sample 8 nb + g][component 8 cb + 2 tq + e] ----
-    // Three phases over the whole tile (log-pdfs and their stores; maxima; exponentials and sums), so that the
-    // NB x CB x 2 exponentials of a lane are independent instruction streams the scheduler can interleave.
+    // Phase 1, whole tile: log-pdfs (they replace q in acc), gamma / E, running maxima, stores of the log-pdfs.
     double mx[NB], m_prev[NB], s_prev[NB];
+    int mkey[NB];
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb) {
-      mx[nb] = a.max_init;
       m_prev[nb] = a.max_init;
       s_prev[nb] = 0.0;
-      if (ma.group > 0) {                                               // running (max, sum) of the earlier groups
+      if (ma.group > 0) {                                               // running (reference point, sum) of the earlier groups
         const int64_t row = row0 + 8 * nb + g;
         if (row < a.n) {
           m_prev[nb] = ma.rowstat[2 * row];
           s_prev[nb] = ma.rowstat[2 * row + 1];
-          mx[nb] = m_prev[nb];
         }
       }
+      mkey[nb] = dkey(m_prev[nb]);
     }
 #pragma unroll
-    for (int cb = 0; cb < CB; ++cb)
+    for (int cb = 0; cb < CB; ++cb) {
+      const int k = 8 * cb + 2 * tq;
+      const bool pad0 = k >= a.kl, pad1 = k + 1 >= a.kl;
+      const double2 c0 = *reinterpret_cast<const double2*>(scl + S0 * KP + 8 * cb);
+      if (a.mode == MODE_GAUSS) {
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int k = 8 * cb + 2 * tq + e;
-        const double* sc = scal_s + k * K1M_SCAL;
-        const bool pad = k >= a.kl;
-        if (a.mode == MODE_GAUSS) {
-          const double c0 = sc[S0];
+        for (int nb = 0; nb < NB; ++nb) {
+          const double l0 = c0.x - 0.5 * clamp0(acc[nb][cb][0]);                         // gauss.pyx:151
+          const double l1 = c0.y - 0.5 * clamp0(acc[nb][cb][1]);
+          acc[nb][cb][0] = pad0 ? -INFINITY : l0;
+          acc[nb][cb][1] = pad1 ? -INFINITY : l1;
+        }
+      } else {
+        const double2 c1 = *reinterpret_cast<const double2*>(scl + S1 * KP + 8 * cb);
+        const double2 c2 = *reinterpret_cast<const double2*>(scl + S2 * KP + 8 * cb);
+        const double2 c3 = *reinterpret_cast<const double2*>(scl + S3 * KP + 8 * cb);
+        const double2 c4 = *reinterpret_cast<const double2*>(scl + S4 * KP + 8 * cb);
 #pragma unroll
-          for (int nb = 0; nb < NB; ++nb) {
-            const double l = c0 - 0.5 * fmax(acc[nb][cb][e], 0.0);                       // gauss.pyx:151
-            acc[nb][cb][e] = pad ? -INFINITY : l;
+        for (int nb = 0; nb < NB; ++nb) {
+          double l[2], ax[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const double c0e = e ? c0.y : c0.x, c1e = e ? c1.y : c1.x, c2e = e ? c2.y : c2.x, c3e = e ? c3.y : c3.x,
+                         c4e = e ? c4.y : c4.x;
+            const double q = clamp0(acc[nb][cb][e]);
+            if (a.mode == MODE_STUDENT_T) {
+              double t = q * c2e;                                                        // student_t.pyx:159-164
+              t += 1.0;
+              t = log(t);
+              t *= c1e;
+              l[e] = t + c0e;
+              ax[e] = c4e / (c3e + q);                                                   // gamma_nk, pmc.pyx:610
+            } else {
+              ax[e] = c3e + c4e * q;                                                     // variational.pyx:798
+              l[e] = c0e + 0.5 * (c1e - c2e - ax[e]);                                    // variational.pyx:691
+            }
           }
-        } else if (a.mode == MODE_STUDENT_T) {
-          const double c0 = sc[S0], c1 = sc[S1], c2 = sc[S2], c3 = sc[S3], c4 = sc[S4];
-#pragma unroll
-          for (int nb = 0; nb < NB; ++nb) {
-            const double q = fmax(acc[nb][cb][e], 0.0);
-            double t = q * c2;                                                           // student_t.pyx:159-164
-            t += 1.0;
-            t = log(t);
-            t *= c1;
-            acc[nb][cb][e] = pad ? -INFINITY : t + c0;
-            if (a.aux_out && !pad && row0 + 8 * nb + g < a.n)                            // gamma_nk, pmc.pyx:610
-              a.aux_out[size_t(row0 + 8 * nb + g) * a.k_out + (contig ? col0 + k : __ldg(a.cols + k))] = c4 / (c3 + q);
-          }
-        } else {
-          const double c0 = sc[S0], c1 = sc[S1], c2 = sc[S2], c3 = sc[S3], c4 = sc[S4];
-#pragma unroll
-          for (int nb = 0; nb < NB; ++nb) {
-            const double x = c3 + c4 * fmax(acc[nb][cb][e], 0.0);                        // variational.pyx:798
-            acc[nb][cb][e] = pad ? -INFINITY : c0 + 0.5 * (c1 - c2 - x);                 // variational.pyx:691
-            if (a.aux_out && !pad && row0 + 8 * nb + g < a.n)
-              a.aux_out[size_t(row0 + 8 * nb + g) * a.k_out + (contig ? col0 + k : __ldg(a.cols + k))] = x;
+          acc[nb][cb][0] = pad0 ? -INFINITY : l[0];
+          acc[nb][cb][1] = pad1 ? -INFINITY : l[1];
+          const int64_t row = row0 + 8 * nb + g;
+          if (a.aux_out && row < a.n) {
+            if (contig) {
+              if (!pad0) *reinterpret_cast<double2*>(a.aux_out + size_t(row) * a.k_out + col0 + k) = make_double2(ax[0], ax[1]);
+            } else {
+              if (!pad0) a.aux_out[size_t(row) * a.k_out + __ldg(a.cols + k)] = ax[0];
+              if (!pad1) a.aux_out[size_t(row) * a.k_out + __ldg(a.cols + k + 1)] = ax[1];
+            }
           }
         }
-#pragma unroll
-        for (int nb = 0; nb < NB; ++nb) mx[nb] = fmax(mx[nb], acc[nb][cb][e]);
       }
-    // log-pdfs leave as 16-byte stores when the output columns are contiguous (VB: log_rho is written normalised below)
-    auto store_pairs = [&](double* out, const double (&v)[NB][CB][2]) {
 #pragma unroll
-      for (int nb = 0; nb < NB; ++nb) {
-        const int64_t row = row0 + 8 * nb + g;
-        if (row >= a.n) continue;
+      for (int nb = 0; nb < NB; ++nb) mkey[nb] = max(mkey[nb], max(dkey(acc[nb][cb][0]), dkey(acc[nb][cb][1])));
+    }
+    // N x K values leave as 16-byte stores when the output columns are contiguous
+    auto store_pairs = [&](double* out, int nb, const double (&v)[CB][2]) {
+      const int64_t row = row0 + 8 * nb + g;
+      if (row >= a.n) return;
 #pragma unroll
-        for (int cb = 0; cb < CB; ++cb) {
-          const int k = 8 * cb + 2 * tq;
-          if (contig) {
-            if (k < a.kl) *reinterpret_cast<double2*>(out + size_t(row) * a.k_out + col0 + k) = make_double2(v[nb][cb][0], v[nb][cb][1]);
-          } else {
+      for (int cb = 0; cb < CB; ++cb) {
+        const int k = 8 * cb + 2 * tq;
+        if (contig) {
+          if (k < a.kl) *reinterpret_cast<double2*>(out + size_t(row) * a.k_out + col0 + k) = make_double2(v[cb][0], v[cb][1]);
+        } else {
 #pragma unroll
-            for (int e = 0; e < 2; ++e)
-              if (k + e < a.kl) out[size_t(row) * a.k_out + __ldg(a.cols + k + e)] = v[nb][cb][e];
-          }
+          for (int e = 0; e < 2; ++e)
+            if (k + e < a.kl) out[size_t(row) * a.k_out + __ldg(a.cols + k + e)] = v[cb][e];
         }
       }
     };
-    if constexpr (SECOND) {
-      if (a.lp_out && a.mode != MODE_VB) store_pairs(a.lp_out, acc);
+    {
+      // mixtures: `individual`; without a fused second pass the raw log-pdfs also wait in resp_out for k1_finish
+      double* const lp_dst = SECOND ? ((a.mode != MODE_VB) ? a.lp_out : nullptr) : (a.lp_out ? a.lp_out : a.resp_out);
+      if (lp_dst) {
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) store_pairs(lp_dst, nb, acc[nb]);
+      }
+    }
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+      mkey[nb] = max(mkey[nb], __shfl_xor_sync(0xffffffffu, mkey[nb], 1));
+      mkey[nb] = max(mkey[nb], __shfl_xor_sync(0xffffffffu, mkey[nb], 2));
+      mx[nb] = dkey_value(mkey[nb]);                                    // reference point of the log-sum-exp (see dkey)
+    }
+
+    // Phase 2: the terms w_k exp(lp - max) of a sample block and their sum over the quad (_regularize.pyx:72-81 up to
+    // rounding).  Eval-only: both blocks back to back (independent exponentials); with the fused second pass the
+    // terms of one block are kept for rho / r while the other block waits in acc.
+    auto term = [&](int nb, int cb, int e, double w, bool& deep) -> double {
+      const double d = acc[nb][cb][e] - mx[nb];
+      if constexpr ((DIAG & 1) != 0) return w * fma(d, 1e-3, 1.0);
+      const bool slow = unsigned(__double2hiint(d)) >= kExpSlowHi;     // d <= -707 (padding: -inf, weight 0)
+      deep |= slow && ((wmask >> (2 * cb + e)) & 1u);
+      return __dmul_rn(w, exp_tab(slow ? 0.0 : d, etab));               // (no contraction: the same bits in every instantiation)
+    };
+    auto quad_sum = [&](int nb, double sum) -> double {
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      if (ma.group > 0) sum = fma(s_prev[nb], exp(m_prev[nb] - mx[nb]), sum);
+      return sum;
+    };
+    // eval-only: nothing is kept; a lane that met the deep tail (d <= -707: subnormal results and zeros, as the
+    // library exp gives them) redoes its share of the sum
+    auto terms_sum = [&](int nb) -> double {
+      bool deep = false;
+      double sum = 0.0;
+#pragma unroll
+      for (int cb = 0; cb < CB; ++cb) {
+        const double2 w2 = *reinterpret_cast<const double2*>(scl + S_WEIGHT * KP + 8 * cb);
+        sum += term(nb, cb, 0, w2.x, deep) + term(nb, cb, 1, w2.y, deep);
+      }
+      if (deep) {
+        sum = 0.0;
+#pragma unroll
+        for (int cb = 0; cb < CB; ++cb) {
+          const double2 w2 = *reinterpret_cast<const double2*>(scl + S_WEIGHT * KP + 8 * cb);
+          sum += __dmul_rn(w2.x, exp(acc[nb][cb][0] - mx[nb])) + __dmul_rn(w2.y, exp(acc[nb][cb][1] - mx[nb]));
+        }
+      }
+      return quad_sum(nb, sum);
+    };
+    auto terms_keep = [&](int nb, double (&ex)[CB][2]) -> double {
+      bool deep = false;
+#pragma unroll
+      for (int cb = 0; cb < CB; ++cb) {
+        const double2 w2 = *reinterpret_cast<const double2*>(scl + S_WEIGHT * KP + 8 * cb);
+        ex[cb][0] = term(nb, cb, 0, w2.x, deep);
+        ex[cb][1] = term(nb, cb, 1, w2.y, deep);
+      }
+      if (deep) {
+#pragma unroll
+        for (int cb = 0; cb < CB; ++cb) {
+          const double2 w2 = *reinterpret_cast<const double2*>(scl + S_WEIGHT * KP + 8 * cb);
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const double d = acc[nb][cb][e] - mx[nb];
+            if (unsigned(__double2hiint(d)) >= kExpSlowHi) ex[cb][e] = __dmul_rn(e ? w2.y : w2.x, exp(d));
+          }
+        }
+      }
+      double sum = 0.0;
+#pragma unroll
+      for (int cb = 0; cb < CB; ++cb) sum += ex[cb][0] + ex[cb][1];
+      return quad_sum(nb, sum);
+    };
+    // per-sample results for one row: log q and the sums; returns log q, f0 = 1 / sum and f1 = -log(sum) for the second pass
+    auto finish_row = [&](int64_t row, bool writer, double sum, double m, double& lq, double& f0, double& f1) {
+      lq = 0.0;
+      f0 = 0.0;
+      f1 = 0.0;
+      if (!SECOND && ma.group + 1 < ma.ngroups) {                       // more components to come
+        if (writer) {
+          ma.rowstat[2 * row] = m;
+          ma.rowstat[2 * row + 1] = sum;
+        }
+        return;
+      }
+      const double ls = log(sum);
+      lq = ls + m;                                                      // _regularize.pyx:81
+      if (writer) {
+        const double w_n = a.sw ? __ldg(a.sw + row) : 1.0;
+        part_w += w_n;
+        if (a.logq) a.logq[row] = lq;
+        if (a.mode != MODE_VB) part_a += w_n * lq;                      // pmc.pyx:388-391
+      }
+      if constexpr (SECOND) {
+        f0 = 1.0 / sum;                                                 // variational.pyx:728-755 (and rho below)
+        f1 = -ls;
+      } else if (ma.rowstat && writer) {                                // for k1_finish
+        ma.rowstat[2 * row] = m;
+        ma.rowstat[2 * row + 1] = (a.mode != MODE_VB) ? 1.0 / (exp(lq) + kTiny) : 1.0 / sum;   // pmc.pyx:39-41
+      }
+    };
+    if constexpr (!SECOND) {
+      double sum[NB];
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) sum[nb] = terms_sum(nb);
+      // one logarithm per lane: lanes with odd tq finish the second sample block, lanes tq = 0 / 1 write
+      const int sel = (NB == 2) ? (tq & 1) : 0;
+      const int64_t row = row0 + 8 * sel + g;
+      double lq, f0, f1;
+      finish_row(row, tq < NB && row < a.n, sel ? sum[NB - 1] : sum[0], sel ? mx[NB - 1] : mx[0], lq, f0, f1);
     } else {
-      // no fused second pass: like the DFMA forms, raw log-pdfs go to lp_out, or wait in resp_out for k1_finish
-      double* const scratch = a.lp_out ? a.lp_out : a.resp_out;
-      if (scratch) store_pairs(scratch, acc);
-    }
-    // weighted log-sum-exp over the components (same value as _regularize.pyx:72-81 up to rounding)
 #pragma unroll
-    for (int nb = 0; nb < NB; ++nb) {
-      mx[nb] = fmax(mx[nb], __shfl_xor_sync(0xffffffffu, mx[nb], 1));
-      mx[nb] = fmax(mx[nb], __shfl_xor_sync(0xffffffffu, mx[nb], 2));
-    }
-    double ex[SECOND ? NB : 1][CB][2], sum[NB];
+      for (int nb = 0; nb < NB; ++nb) {
+        double ex[CB][2], lq, f0, f1;
+        const double sum = terms_keep(nb, ex);
+        finish_row(row0 + 8 * nb + g, tq == nb && row0 + 8 * nb + g < a.n, sum, mx[nb], lq, f0, f1);
+        if (a.mode != MODE_VB) {
+          // rho_nk = exp(lp_nk) w_k / (exp(log q_n) + tiny)  (pmc.pyx:39-41)  = [w_k exp(lp_nk - m)] / sum_j [w_j exp(lp_nj - m)]
+          // as long as neither exponential of the reference's formula leaves the normal range and tiny is negligible
+          // beside exp(log q); where exp(lp_nk) is subnormal (lp < -700), exp(log q) overflows or log q < -650 (tiny /
+          // exp(log q) > 1e-26), the literal formula reproduces the reference's own rounding
+          const bool literal_row = mx[nb] > 700.0 || lq < -650.0;
+          bool literal = literal_row;
 #pragma unroll
-    for (int nb = 0; nb < NB; ++nb) sum[nb] = 0.0;
+          for (int cb = 0; cb < CB; ++cb)
 #pragma unroll
-    for (int cb = 0; cb < CB; ++cb)
+            for (int e = 0; e < 2; ++e) {
+              literal |= unsigned(__double2hiint(acc[nb][cb][e])) >= 0xC085E000u;      // lp <= -700 (padding: -inf)
+              ex[cb][e] *= f0;
+            }
+          if (literal) {
+            const double g0 = 1.0 / (exp(lq) + kTiny);
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const double wk = scal_s[(8 * cb + 2 * tq + e) * K1M_SCAL + S_WEIGHT];
+            for (int cb = 0; cb < CB; ++cb)
 #pragma unroll
-        for (int nb = 0; nb < NB; ++nb) {
-          const double t = wk * exp(acc[nb][cb][e] - mx[nb]);
-          if constexpr (SECOND) ex[nb][cb][e] = t;
-          sum[nb] += t;
-        }
-      }
-#pragma unroll
-    for (int nb = 0; nb < NB; ++nb) {
-      sum[nb] += __shfl_xor_sync(0xffffffffu, sum[nb], 1);
-      sum[nb] += __shfl_xor_sync(0xffffffffu, sum[nb], 2);
-      if (ma.group > 0) sum[nb] = fma(s_prev[nb], exp(m_prev[nb] - mx[nb]), sum[nb]);
-    }
-    // ---- per-sample results: lane tq == nb % 4 of the quad finishes sample nb and hands the quad what the
-    //      second pass needs (the DFMA forms leave that pass to k1_finish; here the log-pdfs are still in registers) ----
-    constexpr bool second = SECOND;     // host: (resp_out != null) || (mode == VB && lp_out != null)
-    double f0[NB], f1[NB];          // mixtures: 1 / (exp(log q) + tiny), exp(max) * that;  VB: 1 / norm, ln(1 / norm)
-#pragma unroll
-    for (int nb = 0; nb < NB; ++nb) {
-      const int64_t row = row0 + 8 * nb + g;
-      f0[nb] = 0.0;
-      f1[nb] = 0.0;
-      if (tq == (nb & 3)) {
-        if (!SECOND && ma.group + 1 < ma.ngroups) {                     // more components to come
-          if (row < a.n) {
-            ma.rowstat[2 * row] = mx[nb];
-            ma.rowstat[2 * row + 1] = sum[nb];
+              for (int e = 0; e < 2; ++e)
+                if (acc[nb][cb][e] < -700.0 || literal_row)
+                  ex[cb][e] = exp(acc[nb][cb][e]) * scl[S_WEIGHT * KP + 8 * cb + e] * g0;
           }
+          store_pairs(a.resp_out, nb, ex);
         } else {
-          const double lq = log(sum[nb]) + mx[nb];                      // _regularize.pyx:81
-          if (row < a.n) {
-            const double w_n = a.sw ? __ldg(a.sw + row) : 1.0;
-            part_w += w_n;
-            if (a.logq) a.logq[row] = lq;
-            if (a.mode != MODE_VB) part_a += w_n * lq;                  // pmc.pyx:388-391
-            if (!SECOND && ma.rowstat) {                                // for k1_finish
-              ma.rowstat[2 * row] = mx[nb];
-              ma.rowstat[2 * row + 1] = (a.mode != MODE_VB) ? 1.0 / (exp(lq) + kTiny)   // pmc.pyx:39-41
-                                                            : 1.0 / sum[nb];            // variational.pyx:728-755
-            }
-          }
-          if (second) {
-            if (a.mode != MODE_VB) {
-              f0[nb] = 1.0 / (exp(lq) + kTiny);                         // pmc.pyx:39-41
-              f1[nb] = exp(mx[nb]) * f0[nb];
-            } else {
-              f0[nb] = 1.0 / sum[nb];                                   // variational.pyx:728-755
-              f1[nb] = log(f0[nb]);
-            }
-          }
-        }
-      }
-      if (second) {
-        f0[nb] = __shfl_sync(0xffffffffu, f0[nb], (lane & ~3) | (nb & 3));
-        f1[nb] = __shfl_sync(0xffffffffu, f1[nb], (lane & ~3) | (nb & 3));
-      }
-    }
-    if constexpr (SECOND) {
-      if (a.mode != MODE_VB) {
-        // rho_nk = exp(lp_nk) w_k / (exp(log q_n) + tiny) = [w_k exp(lp_nk - max)] [exp(max) / (exp(log q_n) + tiny)];
-        // where exp(lp_nk) is subnormal the reference's own rounding is reproduced by its literal formula
-#pragma unroll
-        for (int cb = 0; cb < CB; ++cb)
-#pragma unroll
-          for (int e = 0; e < 2; ++e)
-#pragma unroll
-            for (int nb = 0; nb < NB; ++nb) {
-              double r = ex[nb][cb][e] * f1[nb];
-              if (acc[nb][cb][e] < -700.0 || mx[nb] > 700.0)
-                r = exp(acc[nb][cb][e]) * scal_s[(8 * cb + 2 * tq + e) * K1M_SCAL + S_WEIGHT] * f0[nb];
-              ex[nb][cb][e] = r;
-            }
-        store_pairs(a.resp_out, ex);
-      } else {
-#pragma unroll
-        for (int nb = 0; nb < NB; ++nb) {
           const int64_t row = row0 + 8 * nb + g;
           const double w_r = (a.sw && row < a.n) ? __ldg(a.sw + row) : 1.0;
           double s_rl = 0.0;
@@ -391,17 +542,17 @@ __global__ void __launch_bounds__(NW * 32, 1) k1_mma_eval(const MmaArgs ma) {
           for (int cb = 0; cb < CB; ++cb)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-              double rv = ex[nb][cb][e] * f0[nb];
+              double rv = ex[cb][e] * f0;
               if (rv == 0.0) rv = kTiny;                                              // variational.pyx:753-754
-              const double lrn = (acc[nb][cb][e] - mx[nb]) + f1[nb];                  // variational.pyx:741,755
-              ex[nb][cb][e] = rv;
+              const double lrn = (acc[nb][cb][e] - mx[nb]) + f1;                      // variational.pyx:741,755
+              ex[cb][e] = rv;
               acc[nb][cb][e] = lrn;
               if (8 * cb + 2 * tq + e < a.kl) s_rl = fma(w_r * rv, lrn, s_rl);        // variational.pyx:1003-1013
             }
           if (row < a.n) part_a += s_rl;
+          if (a.resp_out) store_pairs(a.resp_out, nb, ex);
+          if (a.lp_out) store_pairs(a.lp_out, nb, acc[nb]);
         }
-        if (a.resp_out) store_pairs(a.resp_out, ex);
-        if (a.lp_out) store_pairs(a.lp_out, acc);
       }
     }
   }

@@ -71,10 +71,18 @@ __global__ void __launch_bounds__(128) k1_prepare(const double* __restrict__ rec
 
 
 // ---------------------------------------------------------------------------------------------
-// k1_mma_prepare: one CTA per (padded) component: theta_k from the derived record [T | -b | scalars].
+// k1_mma_prepare: one CTA per (padded) component: theta_k from the derived record [T | -b | scalars], and the last
+// word on whether the matrix-instruction form may run.  The expanded quadratic form cancels terms of size
+//     A_k = sum_f |theta_kf| |phi_f(d_k)| = |b_k|^2 + 2 sum_i |(T^T b)_i| |d_i| + sum_{j<=i} c_ij |M_ij| |d_i| |d_j|
+// (d_k = mu_k - c) where q may be O(D); A_k equals |b_k|^2 for a well-conditioned component but grows to kappa |b_k|^2
+// when the offset lies along a wide axis of an ill-conditioned covariance -- k1_prepare's |b_k|^2 test cannot see that.
+// The absolute error of q is ~ sqrt(F) eps A_k, and q enters the exponent with the factor s_k = 1/2 (Gauss),
+// (nu + D) / (2 nu) at most (Student-t), nu_k / 2 (VB, where T^T T = W_k only): the form is refused (flag[1] <- 0, the
+// DFMA form k1_fast_eval takes the launch) unless 2 s_k A_k <= kMmaMaxBias2 for every component.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k1_mma_prepare(const double* __restrict__ derived, int kl, int KP, int d, int dp,
-                                                      int steps, double* __restrict__ theta_all, const int* __restrict__ flag) {
+__global__ void __launch_bounds__(256) k1_mma_prepare(const double* __restrict__ derived, const double* __restrict__ records,
+                                                      const double* __restrict__ shift, int kl, int KP, int d, int dp,
+                                                      int steps, int mode, double* __restrict__ theta_all, int* __restrict__ flag) {
   if (flag[0] != 0 || flag[1] == 0) return;
   // block b = (component group, slot in the group); theta of group g is [steps][KP][4] at g * steps * KP * 4
   const int grp = blockIdx.x / KP, slot = blockIdx.x - grp * KP, k = grp * KP + slot, tid = threadIdx.x;
@@ -85,14 +93,17 @@ __global__ void __launch_bounds__(256) k1_mma_prepare(const double* __restrict__
     return;
   }
   __shared__ double Ts[PMC_MAX_DP * PMC_MAX_DP];                        // dense T, row stride dp
-  __shared__ double bs[PMC_MAX_DP], gs[PMC_MAX_DP];
-  __shared__ double b2;
+  __shared__ double bs[PMC_MAX_DP], gs[PMC_MAX_DP], ds[PMC_MAX_DP];
+  __shared__ double b2, red[8];
   const double* rec = derived + size_t(k) * rl;
   for (int e = tid; e < dp * dp; e += blockDim.x) {
     const int i = e / dp, j = e - i * dp;
     Ts[e] = (j <= i) ? rec[2 * (i >> 1) * ((i >> 1) + 1) + 4 * (j >> 1) + 2 * (i & 1) + (j & 1)] : 0.0;
   }
-  for (int i = tid; i < dp; i += blockDim.x) bs[i] = -rec[nt + i];
+  for (int i = tid; i < dp; i += blockDim.x) {
+    bs[i] = -rec[nt + i];
+    ds[i] = (i < d) ? fabs(records[size_t(k) * rl + nt + i] - shift[i]) : 0.0;   // |d_i|
+  }
   __syncthreads();
   for (int i = tid; i < d; i += blockDim.x) {                           // g = T^T b
     double g = 0.0;
@@ -105,18 +116,32 @@ __global__ void __launch_bounds__(256) k1_mma_prepare(const double* __restrict__
     b2 = s;
   }
   __syncthreads();
+  double size = 0.0;                                                    // this thread's share of A_k
   for (int f = tid; f < steps * 4; f += blockDim.x) {
-    double v = 0.0;
-    if (f == 0) v = b2;
-    else if (f <= d) v = -2.0 * gs[f - 1];
+    double v = 0.0, ph = 0.0;
+    if (f == 0) { v = b2; ph = 1.0; }
+    else if (f <= d) { v = -2.0 * gs[f - 1]; ph = ds[f - 1]; }
     else if (f < F) {
       int r, c;
       tri_index(f - 1 - d, r, c);
       double m = 0.0;
       for (int u = r; u < d; ++u) m = fma(Ts[u * dp + r], Ts[u * dp + c], m);     // (T^T T)_rc, c <= r
       v = (r == c) ? m : 2.0 * m;
+      ph = ds[r] * ds[c];
     }
     theta[(size_t(f >> 2) * KP + slot) * 4 + (f & 3)] = v;
+    size = fma(fabs(v), ph, size);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) size += __shfl_xor_sync(0xffffffffu, size, o);
+  if ((tid & 31) == 0) red[tid >> 5] = size;
+  __syncthreads();
+  if (tid == 0) {
+    double A = 0.0;
+    for (int w = 0; w < int(blockDim.x >> 5); ++w) A += red[w];
+    const double* sc = rec + nt + dp;
+    const double s2 = (mode == MODE_GAUSS) ? 1.0 : (mode == MODE_STUDENT_T) ? sc[S4] / sc[S3] : sc[S4];   // 2 s_k
+    if (!(s2 * A <= kMmaMaxBias2)) atomicExch(&flag[1], 0);             // also refuses NaN
   }
 }
 

@@ -108,6 +108,8 @@ struct pmcb200_ctx {
   PinBuf px[2], pw[2], plogq[2], plp[2], presp[2], paux[2];
   cudaEvent_t slot_done[2] = {nullptr, nullptr};
   int64_t launches = 0;
+  // what the last device-pointer K1 launch offered (pmcb200_last_k1_kernel)
+  int last_dp = 0, last_groups = 0, last_cb = 0, last_nb = 0, last_second = 0;
 };
 
 static int ensure(DevBuf& b, size_t bytes) {
@@ -286,9 +288,10 @@ static int eval_prepare(pmcb200_ctx* c, DevBuf& prep, const EvalArgs& a, cudaStr
   out->mma = K1Launch::MmaPlan();
   if (want_mma) {
     for (int g = 0; g < plan.groups; ++g) {            // theta per component group
-      k1_mma_prepare<<<8 * plan.cb[g], 256, 0, st>>>(base + off_rec + size_t(plan.k0[g]) * rl, plan.count[g], 8 * plan.cb[g],
-                                                     a.d, dp, plan.steps, base + off_theta + plan.theta_off[g],
-                                                     reinterpret_cast<const int*>(base + off_flag));
+      k1_mma_prepare<<<8 * plan.cb[g], 256, 0, st>>>(base + off_rec + size_t(plan.k0[g]) * rl, a.records + size_t(plan.k0[g]) * rl,
+                                                     base + off_shift, plan.count[g], 8 * plan.cb[g], a.d, dp, plan.steps,
+                                                     a.mode, base + off_theta + plan.theta_off[g],
+                                                     reinterpret_cast<int*>(base + off_flag));
       PMC_CUDA_CHECK(cudaGetLastError());
       c->launches++;
     }
@@ -321,6 +324,11 @@ static int eval_launch(pmcb200_ctx* c, const K1Launch& prep, DevBuf& rowbuf, con
   const int ts = k1_tile_rows(dp);
   const int64_t tiles = (a0.n + ts - 1) / ts;
   const int grid = int(std::min<int64_t>(tiles, c->sm_count));
+  if (&rowbuf == &c->k1row) {
+    const bool fused = second_pass && l.mma.groups == 1;
+    c->last_dp = dp; c->last_groups = l.mma.groups; c->last_cb = l.mma.groups ? l.mma.cb[0] : 0;
+    c->last_nb = l.mma.groups ? k1_mma_nb(l.mma.cb[0], fused) : 0; c->last_second = fused ? 1 : 0;
+  }
   if (l.mma.groups > 0) {
     const int em = k1_mma_launch(l, c->sm_count, st);
     if (em != 0) {
@@ -744,6 +752,22 @@ int pmcb200_fp64_peak(pmcb200_ctx* c, int which, int iters, double* gflops_out, 
   const double fma = (which == 3) ? (threads / 32.0) * 64.0 * 256.0 * iters : threads * 64.0 * iters;
   if (gflops_out) *gflops_out = 2.0 * fma / (best * 1e-3) * 1e-9;
   if (ms_out) *ms_out = best;
+  return 0;
+}
+
+int pmcb200_last_k1_kernel(pmcb200_ctx* c, char* buf, int len) {
+  PMC_REQUIRE(c != nullptr && buf != nullptr && len > 0, "last_k1_kernel: bad arguments");
+  buf[0] = 0;
+  if (!c->k1ws.p || c->last_dp == 0) return 0;                       // nothing launched yet
+  PMC_CUDA_CHECK(cudaSetDevice(c->device));
+  PMC_CUDA_CHECK(cudaDeviceSynchronize());
+  int flag[2] = {0, 0};
+  PMC_CUDA_CHECK(cudaMemcpy(flag, c->k1ws.p, sizeof(flag), cudaMemcpyDeviceToHost));
+  if (flag[0] != 0) snprintf(buf, size_t(len), "k1_mixture_eval<%d>", c->last_dp);
+  else if (flag[1] != 0 && c->last_groups > 0)
+    snprintf(buf, size_t(len), "k1_mma_eval<%d, %d, 16, %s>%s", c->last_cb, c->last_nb, c->last_second ? "true" : "false",
+             c->last_groups > 1 ? " (component groups)" : "");
+  else snprintf(buf, size_t(len), "k1_fast_eval<%d>", c->last_dp);
   return 0;
 }
 

@@ -66,8 +66,8 @@ class MixtureDensity(ProbabilityDensity):
         mode = self._kernel_mode()
         if mode is None:
             raise NotImplementedError(
-                "pypmc_b200 evaluates mixtures whose components are all Gauss or all StudentT on the GPU; "
-                "other component types are outside the accelerated path and there is no CPU fallback")
+                "this operation (device-side propose / PMC update) needs a mixture whose components are all Gauss or all "
+                "StudentT; mixtures of other kinds can only be evaluated (MixtureDensity.multi_evaluate)")
         if self.dim > _lib.MAX_DIM:
             raise NotImplementedError("dimension %d exceeds the CUDA kernels' maximum of %d" % (self.dim, _lib.MAX_DIM))
         return mode
@@ -100,7 +100,9 @@ class MixtureDensity(ProbabilityDensity):
         if individual is not None:
             assert len(x) == len(individual), "For the provided ``x``, ``individual`` must have shape %s" % ((n, k),)
             assert individual.shape[1] == k, "For the provided ``x``, ``individual`` must have shape %s" % ((n, k),)
-        mode = self._require_mode()
+        mode = self._kernel_mode()
+        if mode is None or self.dim > _lib.MAX_DIM:
+            return self._multi_evaluate_generic(x, out, individual, components)
         assert (self.weights >= 0.0).all(), "Found negative weight"
         on_device = _dev.is_device_tensor(x)
         t = _dev.torch() if on_device else None
@@ -141,6 +143,58 @@ class MixtureDensity(ProbabilityDensity):
             return out
         return res
 
+    def _multi_evaluate_generic(self, x, out, individual, components):
+        """Mixtures that are not all-Gauss or all-StudentT (mixed kinds, user-defined densities): mixture.pyx:138-156
+        as written -- every component fills its column of ``individual`` through its OWN ``multi_evaluate``, then the
+        weighted log-sum-exp.  Gauss and StudentT components still go through kernel K1 (one launch per kind); a
+        user density runs whatever it implements (the per-point loop of base.py:42-50 if nothing else), which is the
+        reference's contract for such components (mixture_test.py:15-23, 82-104)."""
+        from ..tools._regularize import logsumexp2D
+        n, k = x.shape[0], len(self)
+        on_device = _dev.is_device_tensor(x)
+        xh = x.cpu().numpy() if on_device else x
+        ks = list(range(k)) if components is None else [int(c) for c in components]
+        if components is not None:
+            assert out is None, 'If ``components`` is not None, ``out`` must be None.'
+            if not ks:
+                return None
+        elif out is not None:
+            assert len(out) == n, '``out`` must have length %i' % n
+        host_ind = isinstance(individual, _np.ndarray)
+        ind = individual if (host_ind and individual.dtype == _np.float64) else _np.empty((n, k))
+        if individual is not None and ind is not individual and components is not None:
+            ind[:] = individual.cpu().numpy() if _dev.is_device_tensor(individual) else individual   # untouched columns survive
+        rest = list(ks)
+        if self.dim <= _lib.MAX_DIM:
+            for kind, kmode in ((Gauss, _lib.MODE_GAUSS), (StudentT, _lib.MODE_STUDENT_T)):
+                idx = [j for j in ks if isinstance(self.components[j], kind)]
+                if idx and n > 0:
+                    tmp = _np.empty((n, len(idx)))
+                    run_k1(_np.ascontiguousarray(xh), self._packed(idx, compact=True), len(idx), kmode, lp=tmp)
+                    ind[:, idx] = tmp
+                rest = [j for j in rest if j not in idx]
+        for j in rest:
+            col = _np.empty(n)
+            self.components[j].multi_evaluate(xh, col)
+            ind[:, j] = col
+        if individual is not None and ind is not individual:
+            if _dev.is_device_tensor(individual):
+                individual.copy_(_dev.torch().from_numpy(ind))
+            else:
+                individual[:] = ind
+        if components is not None:
+            return None
+        res = logsumexp2D(ind, self.weights)
+        if on_device:
+            res = _dev.torch().from_numpy(res).to(x.device)
+        if out is not None:
+            if _dev.is_device_tensor(out):
+                out.copy_(res if on_device else _dev.torch().from_numpy(res))
+            else:
+                out[:] = res.cpu().numpy() if on_device else res
+            return out
+        return res
+
     def propose(self, N=1, rng=_np.random.mtrand, trace=False, shuffle=True):
         """Draw ``N`` points (mixture.pyx:159-212): multinomial counts per component, component draws in
         component order, then either the origin array (``trace``) or an in-place shuffle (``shuffle``)."""
@@ -174,7 +228,8 @@ class MixtureDensity(ProbabilityDensity):
             raise ValueError('Either ``shuffle`` or ``trace`` must be ``False``!')
         mode = self._require_mode()
         t = _dev.torch()
-        dev = "cuda:%d" % (_lib.default_device() if device is None else device)
+        device = _lib.default_device() if device is None else int(device)
+        dev = "cuda:%d" % device
         counts = _np.asarray(rng.multinomial(N, self.weights), dtype=_np.int64)
         starts = _np.concatenate([[0], _np.cumsum(counts)]).astype(_np.int64)
         if seed is None:
@@ -190,7 +245,7 @@ class MixtureDensity(ProbabilityDensity):
         x = t.empty((N, d), dtype=t.float64, device=dev)
         latent = t.empty(N, dtype=t.int32, device=dev) if trace else None
         _lib.Context.get(device).mixture_propose(N, d, k, means, chol, dofs, starts, seed, index0, x, d, latent,
-                                                 _dev.current_stream_ptr())
+                                                 _dev.current_stream_ptr(device))
         if trace:
             return x, latent.to(t.int64)
         if shuffle:

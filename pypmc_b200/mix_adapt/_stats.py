@@ -40,8 +40,12 @@ class PacketLayout:
                     sumw=float(packet[self.off_sumw]), sum_a=float(packet[self.off_sum_a]))
 
 
-#: largest squared Mahalanobis distance (mu_k - c)^T Sigma_k^-1 (mu_k - c) tolerated between a component and the
-#: shift c its raw moments are taken about: the covariance then carries ~eps * 1e4 = 2e-12 relative rounding error
+#: largest size of the cancelling terms, sum_ij |P_k,ij| |d_i| |d_j| with d = mu_k - c and P_k = Sigma_k^-1, tolerated
+#: between a component and the shift c its raw moments are taken about.  The recovered covariance carries an absolute
+#: error of ~eps |d|^2 per entry; measured in units of the component's own width (the smallest eigenvalue sees
+#: eps |d|^2 lambda_max(P_k)) that is eps times this bound -- which, unlike the plain Mahalanobis distance
+#: d^T P_k d, also grows when the offset lies along a WIDE axis of an ill-conditioned covariance.  <= 1e4 keeps the
+#: relative rounding error of every covariance below ~2e-12.
 SHIFT_CONDITION_LIMIT = 1.0e4
 
 
@@ -49,7 +53,7 @@ def shift_groups(centers, precisions, weights, live, limit=SHIFT_CONDITION_LIMIT
     """Partition the live components into groups that share one shift vector for kernel K2.
 
     K2 accumulates raw second moments about a shift c; the covariance of component k recovered from them loses
-    about eps * q_k(c), q_k(c) = (mu_k - c)^T P_k (mu_k - c), to cancellation (the reference centres every component
+    about eps * q_k(c), q_k(c) = |mu_k - c|^T |P_k| |mu_k - c| (see SHIFT_CONDITION_LIMIT), to cancellation (the reference centres every component
     on its own new mean, pmc.pyx:200-204 / variational.pyx:876-890, and has no such term).  Normally ONE group --
     shift = weighted centre of the mixture -- keeps every q_k below ``limit`` and K2 runs once.  Components that
     are far apart in units of their own width are put into separate groups, greedily in component order, and K2
@@ -71,8 +75,8 @@ def shift_groups(centers, precisions, weights, live, limit=SHIFT_CONDITION_LIMIT
     def worst(idx, c):
         q = 0.0
         for k in idx:
-            d = centers[k] - c
-            q = max(q, float(d @ precisions[k] @ d))
+            d = np.abs(np.asarray(centers[k], dtype=float) - c)
+            q = max(q, float(d @ np.abs(precisions[k]) @ d))
         return q
 
     c_all = centre(live)
@@ -96,12 +100,15 @@ def grouped_suffstats(ctx, ds, lay, packet, groups, rho, gamma, stream):
     shift array [K, D] the rows refer to (zeros for components in no group)."""
     from .. import _device as dev
     K, D, N = lay.K, lay.D, ds.N
+    index = ds.x.device.index                               # the device the samples live on
+    ctx = type(ctx).get(index)
+    stream = dev.current_stream_ptr(index)
     shifts = np.zeros((K, D))
     ldx = ds.x.stride(0) if N > 1 else D
     if len(groups) == 1 and len(groups[0][0]) > 0 and _is_full(groups[0][0], K):
         idx, c = groups[0]
         shifts[:] = c
-        ctx.suffstats(ds.x, N, ldx, D, dev.to_device(c), rho, gamma, K, K, ds.w, packet, stream)
+        ctx.suffstats(ds.x, N, ldx, D, dev.to_device(c, index), rho, gamma, K, K, ds.w, packet, stream)
         return shifts
     t = dev.torch()
     rows = packet[:lay.stats_len].view(K, lay.row)
@@ -111,7 +118,7 @@ def grouped_suffstats(ctx, ds, lay, packet, groups, rho, gamma, stream):
         rho_g = rho.index_select(1, cols).contiguous()
         gamma_g = None if gamma is None else gamma.index_select(1, cols).contiguous()
         out = t.empty((len(idx), lay.row), dtype=t.float64, device=rho.device)
-        ctx.suffstats(ds.x, N, ldx, D, dev.to_device(c), rho_g, gamma_g, len(idx), len(idx), ds.w, out, stream)
+        ctx.suffstats(ds.x, N, ldx, D, dev.to_device(c, index), rho_g, gamma_g, len(idx), len(idx), ds.w, out, stream)
         rows[cols] = out
         shifts[idx] = c
     return shifts

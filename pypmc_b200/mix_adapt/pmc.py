@@ -42,9 +42,10 @@ class DeviceSamples(object):
         else:
             t = _dev.torch()
             self.latent = latent.to(t.int64) if _dev.is_device_tensor(latent) else _dev.to_device(_np.asarray(latent, dtype=_np.int64))
+        self._src_weights, self._src_latent = weights, latent     # what the caller handed in (identity check in _pmc_update)
         self.rho = None      # [N, K] responsibilities of the last E-pass (device)
         self.gamma = None    # [N, K] Student-t gamma of the last E-pass (device)
-        self.epass = None    # (K, live, mode, record fingerprint, local sums[2]) of an E-pass computed ahead (PMC.run)
+        self.epass = None    # (K, live, mode, record fingerprint, local sums[2], mixture weights) of an E-pass computed ahead
 
     def weigh(self, proposal, log_target):
         """Importance weights w_n = exp(log_target_n - log q(x_n)) of these samples under ``proposal`` (extension).
@@ -70,8 +71,9 @@ class DeviceSamples(object):
         run_k1(self.x, packed, K, mode, logq=logq, resp=self.rho, aux=self.gamma if student else None)
         lt = log_target if _dev.is_device_tensor(log_target) else _dev.to_device(_np.asarray(log_target, dtype=_np.float64))
         self.w = t.exp(lt - logq)
+        self._src_weights = self.w
         sums = t.stack([(self.w * logq).sum(), self.w.sum()])       # what K1 would have left in the packet
-        self.epass = (K, tuple(live), mode, _fingerprint(packed), sums)
+        self.epass = (K, tuple(live), mode, _fingerprint(packed), sums, _np.array(proposal.weights, dtype=float))
         return self.w
 
 
@@ -103,7 +105,10 @@ def _e_pass_and_stats(ds, density, live, rb, mode):
 
     ahead = ds.epass
     ds.epass = None
-    reuse = bool(live) and rb and ahead is not None and ahead[:4] == (K, tuple(live), mode, _fingerprint(packed))
+    # a pass computed ahead serves this update only if it was made with the same components AND the same mixture weights
+    # (up to the 1 +- 1e-16 rescaling of normalize(), which is why the weights are not part of the fingerprint)
+    reuse = bool(live) and rb and ahead is not None and ahead[:4] == (K, tuple(live), mode, _fingerprint(packed)) \
+        and _np.allclose(ahead[5], density.weights, rtol=1e-13, atol=0.0)
     if not reuse:
         _alloc_e_buffers(ds, N, K, len(live), student)
     gamma = ds.gamma if student else None
@@ -175,7 +180,7 @@ def e_pass_ahead(ds, density, mode):
     sums = t.zeros(2, dtype=t.float64, device=ds.x.device)
     packed = density._packed(live)
     run_k1(ds.x, packed, K, mode, resp=ds.rho, aux=ds.gamma if student else None, weights=ds.w, sums=sums)
-    ds.epass = (K, tuple(live), mode, _fingerprint(packed), sums.clone())
+    ds.epass = (K, tuple(live), mode, _fingerprint(packed), sums.clone(), _np.array(density.weights, dtype=float))
     _parallel.allreduce_(sums)
     s = sums.cpu().numpy()
     return float(s[0] / s[1])
@@ -224,16 +229,23 @@ def _apply_update(density, live, alpha, mean, cov, new_dof=None):
 
 
 def _as_device_samples(samples, weights, latent):
+    """``samples`` as :class:`DeviceSamples`.  A DeviceSamples object carries its own weights and latent indices; explicit
+    ``weights`` / ``latent`` next to it must be the very objects it was built from (PMC passes them along), anything
+    else is a contradiction the caller has to resolve."""
     if isinstance(samples, DeviceSamples):
+        for name, given, own in (("weights", weights, samples._src_weights), ("latent", latent, samples._src_latent)):
+            if given is not None and given is not own:
+                raise ValueError("`%s` was passed next to a DeviceSamples object that carries its own %s; "
+                                 "put them into the DeviceSamples instead" % (name, name))
         return samples
     return DeviceSamples(samples, weights, latent)
 
 
 def _pmc_update(samples, density, weights, latent, rb, mincount, copy, mode, dof_args=None):
-    _check_arguments(samples, weights, latent, mincount, rb)
+    ds = _as_device_samples(samples, weights, latent)
+    _check_arguments(samples, weights, ds.latent, mincount, rb)       # the latent indices that will actually be used
     if copy:
         density = _cp(density)
-    ds = _as_device_samples(samples, weights, latent)
     if not isinstance(density, MixtureDensity) or density._require_mode() != mode:
         raise TypeError("``density`` must be a MixtureDensity with %s components"
                         % ("StudentT" if mode == _lib.MODE_STUDENT_T else "Gauss"))

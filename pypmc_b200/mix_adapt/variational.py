@@ -253,8 +253,8 @@ class GaussianInference(object):
         self.N_comp = st["A"]
         if not _np.isfinite(self.N_comp).any():
             raise _np.linalg.LinAlgError('Encountered inf or nan in update of responsibilities\n' + str(self.N_comp))
-        N_reg, self.x_mean_comp, self.S = moments_from_stats(st, shift, "B")
-        self.inv_N_comp = 1. / N_reg                                   # variational.pyx:699-709
+        self.N_comp, self.x_mean_comp, self.S = moments_from_stats(st, shift, "B")   # N_comp regularised in place like
+        self.inv_N_comp = 1. / self.N_comp                             # variational.pyx:699-709 (exact zeros -> tiny)
         if not _np.isfinite(self.S).any():
             raise _np.linalg.LinAlgError('Encountered inf or nan in update of sample covariance\n' + str(self.S))
         self._expectation_log_q_Z = st["sum_a"]                        # variational.pyx:1003-1013

@@ -106,6 +106,39 @@ def gauss_case(name, N, K, D, ridge=0.5, dead=(), full=True, keep_rows=None):
     print(name, "cond(cov0) = %.3g" % np.linalg.cond(covs[0]))
 
 
+def illcond_case(name="gauss_illcond", N=1536, K=16, D=8, narrow=1e-5, spread=30.0):
+    """ill-conditioned covariances (one axis 1e5 times narrower in variance than the others, kappa = 1e5)
+    whose centres are offset from the mixture's centre along the WIDE axes.  The Mahalanobis distance of the offsets
+    stays moderate (|b_k|^2 ~ 6e3) while the terms of a quadratic form expanded about the common centre are ~kappa
+    times larger -- the case a |b|^2-based guard of the expanded (matrix-instruction) form cannot see."""
+    rng = np.random.default_rng(41)
+    q, _ = np.linalg.qr(rng.normal(size=(D, D)))                 # common axes; the last one is the narrow one
+    lam = np.ones(D)
+    lam[-1] = narrow
+    covs = np.array([q @ np.diag(lam * rng.uniform(0.5, 1.5, size=D)) @ q.T for _ in range(K)])
+    covs = 0.5 * (covs + np.swapaxes(covs, 1, 2))
+    coeff = rng.normal(0.0, spread, size=(K, D))
+    coeff[:, -1] = rng.normal(0.0, 3.0 * np.sqrt(narrow), size=K)   # along the narrow axis: a few of ITS sigmas only
+    means = coeff @ q.T
+    w = rng.uniform(0.5, 1.5, size=K)
+    w /= w.sum()
+    x, latent, sw = synth_samples(N, means, covs, seed=43)
+    mix = create_gaussian_mixture(means, covs, w)
+    individual = np.empty((N, K))
+    logq = mix.multi_evaluate(x, individual=individual)
+    out = dict(x=x, latent=latent, sample_weights=sw, means=means, covs=covs, weights=np.array(mix.weights),
+               individual=individual, logq=logq)
+    out.update(pack("pmc_weighted", recover(gaussian_pmc(x, mix, weights=sw))))
+    out.update(pack("pmc_unweighted", recover(gaussian_pmc(x, mix))))
+    out["loglik_weighted"] = np.array(PMC(x, mix, weights=sw).log_likelihood())
+    out["loglik_unweighted"] = np.array(PMC(x, mix).log_likelihood())
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    c = (w[:, None] * means).sum(0)
+    b2 = max(float((m - c) @ np.linalg.inv(s) @ (m - c)) for m, s in zip(means, covs))
+    a = max(float(np.abs(m - c) @ np.abs(np.linalg.inv(s)) @ np.abs(m - c)) for m, s in zip(means, covs))
+    print(name, "cond(cov0) = %.3g, max |b|^2 = %.3g, max |d|^T |P| |d| = %.3g" % (np.linalg.cond(covs[0]), b2, a))
+
+
 def student_case(name, N, K, D, dof=4.0, full=True, keep_rows=None):
     means, covs, w = synth_mixture(K, D)
     x, latent, sw = synth_samples(N, means, covs, dof=dof)
@@ -218,11 +251,15 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "pmc_example":
         pmc_example_case()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "gauss_illcond":
+        illcond_case()
+        sys.exit(0)
     pmc_example_case()
     gauss_case("gauss_small", N=257, K=5, D=7, dead=(3,))
     gauss_case("gauss_c2", N=2048, K=32, D=30, full=False, keep_rows=128)  # BASELINE config 2 shape
     gauss_case("gauss_c2_stress", N=2048, K=32, D=30, ridge=1e-4, full=False, keep_rows=128)  # kappa ~ 3e4
     student_case("student_small", N=301, K=4, D=5)
     student_case("student_c4", N=1600, K=16, D=40, full=False, keep_rows=128)  # BASELINE config 4 shape
+    illcond_case()
     vb_case("vb_small", N=300, K=4, D=3)
     vb_case("vb_c3", N=2048, K=64, D=20, full=False, keep_rows=64)          # BASELINE config 3 shape

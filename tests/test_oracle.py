@@ -109,7 +109,7 @@ def test_gaussian_pmc_reference_golden_tables():
 
 
 # ---------------------------------------------------------------- fixtures from the compiled reference
-@pytest.mark.parametrize("name", ["gauss_small", "gauss_c2", "gauss_c2_stress"])
+@pytest.mark.parametrize("name", ["gauss_small", "gauss_c2", "gauss_c2_stress", "gauss_illcond"])
 def test_gauss_mixture_vs_reference_fixture(golden, name):
     g = golden(name)
     comps = orc.Components(g["means"], g["covs"])
