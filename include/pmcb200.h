@@ -149,6 +149,18 @@ int pmcb200_mixture_propose(pmcb200_ctx* ctx, int64_t n, int d, int k,
                             const int64_t* starts_host, uint64_t seed, uint64_t index0,
                             double* x_dev, int64_t ldx, int* latent_dev, void* stream);
 
+/* ---- K4: importance weights of a run and the weight-vector reductions ---------------------------------
+ * Replaces ImportanceSampler._calculate_weights sampler/importance_sampling.py:197-215 (w_n = exp(log target(x_n) -
+ * log q(x_n)), one Python-level evaluation per sample there) and the N-sized passes of perp / ess
+ * tools/convergence.py:6-72 and of the weighted log-likelihood mix_adapt/pmc.pyx:388-391.
+ * log_target_dev [n] may be NULL: logq_dev then already holds log w.  w_dev [n] may be NULL (sums only).
+ * sums_dev [5] = { sum w, sum w log q, sum w^2, sum w log w, number of nonzero w }  (zero weights contribute nothing to
+ * the logarithmic sums, convergence.py:30-34); with them
+ *   perp = exp(log(S0) - S3 / S0) / n,   ess = S0^2 / (n S2).
+ */
+int pmcb200_importance_weights(pmcb200_ctx* ctx, const double* log_target_dev, const double* logq_dev, int64_t n,
+                               double* w_dev, double* sums_dev, void* stream);
+
 /* ---- measurement helpers ---------------------------------------------------------------------------
  * FP64 FMA throughput of this device (register-resident DFMA chains on every SM), the roof that bounds
  * K1/K2.  which: 0 = DFMA only, 1 = DFMA + one broadcast LDS.128 per 4 DFMA,

@@ -73,6 +73,12 @@ def current_stream_ptr(device=None) -> int:
     return torch().cuda.current_stream(_lib.default_device() if device is None else device).cuda_stream
 
 
+#: device copies of packed records keyed by (device, content): an unchanged mixture evaluated again (every EM step of
+#: PMC.run, every step of a sampler) re-uses its records instead of paying a blocking pageable upload per call
+_RECORD_CACHE = {}
+_RECORD_CACHE_MAX = 32
+
+
 class PackedComponents:
     """Records + output columns of the components to evaluate, on host and (lazily) on device."""
 
@@ -88,5 +94,12 @@ class PackedComponents:
     def device(self, index=None):
         index = _lib.default_device() if index is None else index
         if index not in self._dev:
-            self._dev[index] = (to_device(self.records, index), to_device(self.cols, index))
+            key = (index, self.records.shape, hash(self.records.tobytes()), hash(self.cols.tobytes()))
+            hit = _RECORD_CACHE.pop(key, None)
+            if hit is None:
+                hit = (to_device(self.records, index), to_device(self.cols, index))
+            _RECORD_CACHE[key] = hit                                  # most recently used last
+            while len(_RECORD_CACHE) > _RECORD_CACHE_MAX:
+                _RECORD_CACHE.pop(next(iter(_RECORD_CACHE)))
+            self._dev[index] = hit
         return self._dev[index]

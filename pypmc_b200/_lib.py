@@ -46,6 +46,7 @@ SIGNATURES = {
     "pmcb200_mixture_propose": (ctypes.c_int, [
         _vp, ctypes.c_int64, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp, _vp, ctypes.c_uint64, ctypes.c_uint64, _vp,
         ctypes.c_int64, _vp, _vp]),
+    "pmcb200_importance_weights": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int64, _vp, _vp, _vp]),
     "pmcb200_fp64_peak": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _c_double_p, _c_double_p]),
     "pmcb200_last_k1_kernel": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_int]),
     "pmcb200_launch_count": (ctypes.c_int64, [_vp]),
@@ -165,6 +166,10 @@ class Context:
         _check(load().pmcb200_mixture_propose(self.handle, n, d, k, _ptr(means), _ptr(chol), _ptr(dofs), starts.ctypes.data,
                                               int(seed), int(index0), _ptr(x), ldx, _ptr(latent), stream),
                "pmcb200_mixture_propose")
+
+    def importance_weights(self, log_target, logq, n, w, sums, stream=0):
+        _check(load().pmcb200_importance_weights(self.handle, _ptr(log_target), _ptr(logq), n, _ptr(w), _ptr(sums), stream),
+               "pmcb200_importance_weights")
 
     def fp64_peak(self, which=0, iters=4000):
         g, ms = ctypes.c_double(), ctypes.c_double()

@@ -46,7 +46,8 @@
 namespace pmc {
 
 constexpr double kMmaMaxBias2 = 8.0e4;   // above this size of the cancelling terms (A_k >= 4 |b_k|^2) the DFMA forms run instead
-constexpr int K1M_SCAL = 6;              // scalars per component kept in shared memory (S0..S4, weight), [scalar][KP]
+constexpr int K1M_SCAL = 7;              // scalars per component kept in shared memory (S0..S4, weight, -tau), [scalar][KP]
+constexpr int K1M_TAU = 6;               // row of -tau_k, the significance threshold of a term of the log-sum-exp (see below)
 constexpr int K1M_EXPTAB = 256;          // entries of the 2^(j/256) table
 
 struct MmaArgs {
@@ -150,9 +151,29 @@ __global__ void __launch_bounds__(NW * 32, 1) k1_mma_eval(const MmaArgs ma) {
     double2* dst = reinterpret_cast<double2*>(theta_s);
     for (int i = tid; i < n2; i += blockDim.x) dst[i] = __ldg(src + i);
     const int rl = record_len(dp), so = tri_len(dp) + dp;
-    for (int i = tid; i < KP * K1M_SCAL; i += blockDim.x) {
+    for (int i = tid; i < KP * (K1M_SCAL - 1); i += blockDim.x) {
       const int s = i / KP, k = i - s * KP;
       scal_s[i] = (k < a.kl) ? a.records[size_t(k) * rl + so + s] : 0.0;
+    }
+    // Significance thresholds.  A term w_k exp(lp_k - m) below 2^-66 w_min (w_min = the smallest weight) is below
+    // 2^-66 of the sum -- the component that attains the maximum contributes at least w_min exp(-3e-4) -- so dropping
+    // every such term changes the sum by less than K 2^-66 relative, 1e-18 at K = 64.  With -tau_k = ln(w_min / w_k)
+    // - 45.75 a term is kept iff lp_k - m > -tau_k.  For samples that belong to one or two components of a
+    // separated mixture (the usual case in D >= 10) this leaves one or two exponentials per sample instead of K.
+    // The shortcut needs every weight positive and the maximum taken over the evaluated components only: with zero
+    // weights, max_init = 0 (pmc.pyx:26-27) or component groups, -tau_k = -inf and every finite term is kept.
+    {
+      double wmin = INFINITY;
+      bool ok = (a.max_init == -DBL_MAX) && ma.ngroups == 1;
+      for (int k = 0; k < a.kl; ++k) {
+        const double w = a.records[size_t(k) * rl + so + S_WEIGHT];
+        ok = ok && (w > 0.0) && isfinite(w);
+        wmin = fmin(wmin, w);
+      }
+      for (int k = tid; k < KP; k += blockDim.x) {
+        const double w = (k < a.kl) ? a.records[size_t(k) * rl + so + S_WEIGHT] : 0.0;
+        scal_s[K1M_TAU * KP + k] = (ok && k < a.kl) ? log(wmin / w) - 45.75 : -INFINITY;
+      }
     }
     for (int j = tid; j < dp; j += blockDim.x) cs[j] = (j < D) ? ma.shift[j] : 0.0;
     for (int j = tid; j < K1M_EXPTAB; j += blockDim.x) etab[j] = kExp2Table[j];
@@ -410,11 +431,10 @@ __global__ void __launch_bounds__(NW * 32, 1) k1_mma_eval(const MmaArgs ma) {
     // Phase 2: the terms w_k exp(lp - max) of a sample block and their sum over the quad (_regularize.pyx:72-81 up to
     // rounding).  Eval-only: both blocks back to back (independent exponentials); with the fused second pass the
     // terms of one block are kept for rho / r while the other block waits in acc.
-    auto term = [&](int nb, int cb, int e, double w, bool& deep) -> double {
-      const double d = acc[nb][cb][e] - mx[nb];
+    auto term = [&](double d, double w, bool live, bool& deep) -> double {
       if constexpr ((DIAG & 1) != 0) return w * fma(d, 1e-3, 1.0);
       const bool slow = unsigned(__double2hiint(d)) >= kExpSlowHi;     // d <= -707 (padding: -inf, weight 0)
-      deep |= slow && ((wmask >> (2 * cb + e)) & 1u);
+      deep |= slow && live;
       return __dmul_rn(w, exp_tab(slow ? 0.0 : d, etab));               // (no contraction: the same bits in every instantiation)
     };
     auto quad_sum = [&](int nb, double sum) -> double {
@@ -423,48 +443,92 @@ __global__ void __launch_bounds__(NW * 32, 1) k1_mma_eval(const MmaArgs ma) {
       if (ma.group > 0) sum = fma(s_prev[nb], exp(m_prev[nb] - mx[nb]), sum);
       return sum;
     };
-    // eval-only: nothing is kept; a lane that met the deep tail (d <= -707: subnormal results and zeros, as the
-    // library exp gives them) redoes its share of the sum
-    auto terms_sum = [&](int nb) -> double {
-      bool deep = false;
-      double sum = 0.0;
+    // bit 2 cb + e: the term of component 8 cb + 2 tq + e is significant (d > -tau_k, or a NaN that must propagate)
+    auto significant = [&](int nb, double (&d)[CB][2]) -> unsigned {
+      unsigned sig = 0u;
 #pragma unroll
       for (int cb = 0; cb < CB; ++cb) {
-        const double2 w2 = *reinterpret_cast<const double2*>(scl + S_WEIGHT * KP + 8 * cb);
-        sum += term(nb, cb, 0, w2.x, deep) + term(nb, cb, 1, w2.y, deep);
+        const double2 t2 = *reinterpret_cast<const double2*>(scl + K1M_TAU * KP + 8 * cb);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          d[cb][e] = acc[nb][cb][e] - mx[nb];
+          const unsigned hi = unsigned(__double2hiint(d[cb][e])), thr = unsigned(__double2hiint(e ? t2.y : t2.x));
+          sig |= ((hi < thr || hi > 0xFFF00000u) ? 1u : 0u) << (2 * cb + e);
+        }
+      }
+      return sig;
+    };
+    // eval-only: nothing is kept.  Rounds over the significant terms of the warp: in every round each lane evaluates
+    // its next significant term (none: a zero), so a tile costs max-over-lanes(#significant) exponentials per lane
+    // instead of 2 CB.  The terms are added in component order, like the dense sum of the second-pass instantiation
+    // with the insignificant ones left out -- the two give the same bits.  A lane that met the deep tail (d <= -707:
+    // subnormal results and zeros, as the library exp gives them; only possible with tau = inf) redoes its sum.
+    auto terms_sum = [&](int nb) -> double {
+      double d[CB][2];
+      unsigned sig = significant(nb, d);
+      const unsigned sig0 = sig;
+      bool deep = false;
+      double sum = 0.0;
+      if (__any_sync(0xffffffffu, __popc(sig) > (CB + 1) / 2)) {        // many overlapping components: all terms, straight-line
+#pragma unroll
+        for (int cb = 0; cb < CB; ++cb) {
+          const double2 w2 = *reinterpret_cast<const double2*>(scl + S_WEIGHT * KP + 8 * cb);
+          const double t0 = term(d[cb][0], w2.x, (wmask >> (2 * cb)) & 1u, deep);
+          const double t1 = term(d[cb][1], w2.y, (wmask >> (2 * cb + 1)) & 1u, deep);
+          if (sig & (1u << (2 * cb))) sum += t0;
+          if (sig & (2u << (2 * cb))) sum += t1;
+        }
+        sig = 0u;
+      }
+      while (__any_sync(0xffffffffu, sig != 0u)) {
+        const int idx = __ffs(int(sig)) - 1;                            // -1: this lane has nothing left
+        double dv = 0.0;
+#pragma unroll
+        for (int cb = 0; cb < CB; ++cb) {
+          if (idx == 2 * cb) dv = d[cb][0];
+          if (idx == 2 * cb + 1) dv = d[cb][1];
+        }
+        const double wv = (idx >= 0) ? scl[S_WEIGHT * KP + 8 * (idx >> 1) + (idx & 1)] : 0.0;
+        sum += term(dv, wv, idx >= 0 && ((wmask >> idx) & 1u), deep);
+        sig &= sig - 1u;
       }
       if (deep) {
         sum = 0.0;
 #pragma unroll
         for (int cb = 0; cb < CB; ++cb) {
           const double2 w2 = *reinterpret_cast<const double2*>(scl + S_WEIGHT * KP + 8 * cb);
-          sum += __dmul_rn(w2.x, exp(acc[nb][cb][0] - mx[nb])) + __dmul_rn(w2.y, exp(acc[nb][cb][1] - mx[nb]));
+          if (sig0 & (1u << (2 * cb))) sum += __dmul_rn(w2.x, exp(d[cb][0]));
+          if (sig0 & (2u << (2 * cb))) sum += __dmul_rn(w2.y, exp(d[cb][1]));
         }
       }
       return quad_sum(nb, sum);
     };
+    // fused second pass: every term is needed for rho / r; the sum runs over the significant ones (see terms_sum)
     auto terms_keep = [&](int nb, double (&ex)[CB][2]) -> double {
+      double d[CB][2];
+      const unsigned sig = significant(nb, d);
       bool deep = false;
 #pragma unroll
       for (int cb = 0; cb < CB; ++cb) {
         const double2 w2 = *reinterpret_cast<const double2*>(scl + S_WEIGHT * KP + 8 * cb);
-        ex[cb][0] = term(nb, cb, 0, w2.x, deep);
-        ex[cb][1] = term(nb, cb, 1, w2.y, deep);
+        ex[cb][0] = term(d[cb][0], w2.x, (wmask >> (2 * cb)) & 1u, deep);
+        ex[cb][1] = term(d[cb][1], w2.y, (wmask >> (2 * cb + 1)) & 1u, deep);
       }
       if (deep) {
 #pragma unroll
         for (int cb = 0; cb < CB; ++cb) {
           const double2 w2 = *reinterpret_cast<const double2*>(scl + S_WEIGHT * KP + 8 * cb);
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const double d = acc[nb][cb][e] - mx[nb];
-            if (unsigned(__double2hiint(d)) >= kExpSlowHi) ex[cb][e] = __dmul_rn(e ? w2.y : w2.x, exp(d));
-          }
+          for (int e = 0; e < 2; ++e)
+            if (unsigned(__double2hiint(d[cb][e])) >= kExpSlowHi) ex[cb][e] = __dmul_rn(e ? w2.y : w2.x, exp(d[cb][e]));
         }
       }
       double sum = 0.0;
 #pragma unroll
-      for (int cb = 0; cb < CB; ++cb) sum += ex[cb][0] + ex[cb][1];
+      for (int cb = 0; cb < CB; ++cb) {
+        if (sig & (1u << (2 * cb))) sum += ex[cb][0];
+        if (sig & (2u << (2 * cb))) sum += ex[cb][1];
+      }
       return quad_sum(nb, sum);
     };
     // per-sample results for one row: log q and the sums; returns log q, f0 = 1 / sum and f1 = -log(sum) for the second pass
@@ -543,13 +607,13 @@ __global__ void __launch_bounds__(NW * 32, 1) k1_mma_eval(const MmaArgs ma) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               double rv = ex[cb][e] * f0;
-              if (rv == 0.0) rv = kTiny;                                              // variational.pyx:753-754
+              if (((__double2hiint(rv) & 0x7fffffff) | __double2loint(rv)) == 0) rv = kTiny;   // r == 0 -> tiny, variational.pyx:753-754
               const double lrn = (acc[nb][cb][e] - mx[nb]) + f1;                      // variational.pyx:741,755
               ex[cb][e] = rv;
               acc[nb][cb][e] = lrn;
-              if (8 * cb + 2 * tq + e < a.kl) s_rl = fma(w_r * rv, lrn, s_rl);        // variational.pyx:1003-1013
+              if (8 * cb + 2 * tq + e < a.kl) s_rl = fma(rv, lrn, s_rl);              // variational.pyx:1003-1013
             }
-          if (row < a.n) part_a += s_rl;
+          if (row < a.n) part_a = fma(w_r, s_rl, part_a);
           if (a.resp_out) store_pairs(a.resp_out, nb, ex);
           if (a.lp_out) store_pairs(a.lp_out, nb, acc[nb]);
         }

@@ -11,6 +11,7 @@
 #include "k1_prepare.cuh"
 #include "k2_suffstats.cuh"
 #include "k3_propose.cuh"
+#include "k4_weights.cuh"
 #include "microbench.cuh"
 
 namespace pmc {
@@ -100,6 +101,7 @@ struct pmcb200_ctx {
   DevBuf pws;             // K3: block starts
   DevBuf cws;             // K2: per-CTA partial column sums (gamma)
   DevBuf k1row;           // K1: per-row (max, 1/denominator) handed from k1_fast_eval to k1_finish
+  DevBuf wws;             // K4: arrival counter + per-CTA partial sums
   cudaStream_t copy_stream[2] = {nullptr, nullptr};
   // host pipeline: per-slot device buffers
   DevBuf hx[2], hw[2], hlogq[2], hlp[2], hresp[2], haux[2], hws[2], hsums[2], hrow[2];
@@ -213,7 +215,7 @@ int pmcb200_create(int device, pmcb200_ctx** out) {
 int pmcb200_destroy(pmcb200_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
-  DevBuf* all[] = {&c->ws, &c->k1ws, &c->k1row, &c->pws, &c->cws, &c->hrec, &c->hcols};
+  DevBuf* all[] = {&c->ws, &c->k1ws, &c->k1row, &c->pws, &c->cws, &c->wws, &c->hrec, &c->hcols};
   for (DevBuf* b : all)
     if (b->p) cudaFree(b->p);
   for (int i = 0; i < 2; ++i) {
@@ -713,6 +715,27 @@ int pmcb200_mixture_propose(pmcb200_ctx* c, int64_t n, int d, int k, const doubl
   const int64_t blocks = (n + K3_THREADS - 1) / K3_THREADS;
   const int grid = int(std::min<int64_t>(blocks, int64_t(c->sm_count) * 8));
   k3_propose<<<grid, K3_THREADS, smem, st>>>(a);
+  PMC_CUDA_CHECK(cudaGetLastError());
+  c->launches++;
+  return 0;
+}
+
+int pmcb200_importance_weights(pmcb200_ctx* c, const double* log_target, const double* logq, int64_t n, double* w,
+                               double* sums, void* stream) {
+  PMC_REQUIRE(c != nullptr, "importance_weights: NULL context");
+  PMC_REQUIRE(n >= 0 && sums != nullptr, "importance_weights: bad arguments");
+  PMC_CUDA_CHECK(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (n == 0) {
+    PMC_CUDA_CHECK(cudaMemsetAsync(sums, 0, K4_SUMS * sizeof(double), st));
+    return 0;
+  }
+  PMC_REQUIRE(logq != nullptr, "importance_weights: NULL input");
+  const int grid = int(std::min<int64_t>((n + K4_THREADS - 1) / K4_THREADS, int64_t(c->sm_count) * 8));
+  if (int rc = ensure(c->wws, 16 + size_t(c->sm_count) * 8 * K4_SUMS * sizeof(double))) return rc;   // zeroed at allocation
+  unsigned int* counter = static_cast<unsigned int*>(c->wws.p);
+  double* partials = reinterpret_cast<double*>(static_cast<char*>(c->wws.p) + 16);
+  k4_weights<<<grid, K4_THREADS, 0, st>>>(log_target, logq, n, w, partials, counter, sums);
   PMC_CUDA_CHECK(cudaGetLastError());
   c->launches++;
   return 0;

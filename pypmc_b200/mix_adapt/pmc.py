@@ -46,6 +46,7 @@ class DeviceSamples(object):
         self.rho = None      # [N, K] responsibilities of the last E-pass (device)
         self.gamma = None    # [N, K] Student-t gamma of the last E-pass (device)
         self.epass = None    # (K, live, mode, record fingerprint, local sums[2], mixture weights) of an E-pass computed ahead
+        self.weight_sums = None   # device [5]: sum w, sum w log q, sum w^2, sum w log w, #nonzero (kernel K4, set by weigh())
 
     def weigh(self, proposal, log_target):
         """Importance weights w_n = exp(log_target_n - log q(x_n)) of these samples under ``proposal`` (extension).
@@ -69,12 +70,37 @@ class DeviceSamples(object):
         packed = proposal._packed(live)
         logq = t.empty(N, dtype=t.float64, device=self.x.device)
         run_k1(self.x, packed, K, mode, logq=logq, resp=self.rho, aux=self.gamma if student else None)
-        lt = log_target if _dev.is_device_tensor(log_target) else _dev.to_device(_np.asarray(log_target, dtype=_np.float64))
-        self.w = t.exp(lt - logq)
+        index = self.x.device.index
+        lt = log_target if _dev.is_device_tensor(log_target) else _dev.to_device(_np.asarray(log_target, dtype=_np.float64), index)
+        # K4: the weights and, in the same pass, sum w, sum w log q, sum w^2, sum w log w (perp / ess / likelihood)
+        self.w = t.empty(N, dtype=t.float64, device=self.x.device)
+        self.weight_sums = t.empty(5, dtype=t.float64, device=self.x.device)
+        _lib.Context.get(index).importance_weights(lt.contiguous(), logq, N, self.w, self.weight_sums, _dev.current_stream_ptr(index))
         self._src_weights = self.w
-        sums = t.stack([(self.w * logq).sum(), self.w.sum()])       # what K1 would have left in the packet
+        sums = t.stack([self.weight_sums[1], self.weight_sums[0]])  # what K1 would have left in the packet
         self.epass = (K, tuple(live), mode, _fingerprint(packed), sums, _np.array(proposal.weights, dtype=float))
         return self.w
+
+
+def _weight_quality(ds):
+    """(perp, ess) of the weights formed by :meth:`DeviceSamples.weigh`, from the sums kernel K4 left -- over all
+    ranks' samples when the statistics all-reduce is enabled (tools/convergence.py:6-72)."""
+    if ds.weight_sums is None:
+        raise ValueError("no weights were formed on the device yet: call DeviceSamples.weigh first")
+    s = ds.weight_sums.clone()
+    n = _dev.torch().tensor([float(ds.N)], dtype=s.dtype, device=s.device)
+    _parallel.allreduce_(s)
+    _parallel.allreduce_(n)
+    s, n = s.cpu().numpy(), float(n[0])
+    perp = float(_np.exp(_np.log(s[0]) - s[3] / s[0]) / n)
+    ess = float(s[0] * s[0] / (n * s[2]))
+    return perp, ess
+
+
+DeviceSamples.perp = lambda self: _weight_quality(self)[0]
+DeviceSamples.ess = lambda self: _weight_quality(self)[1]
+DeviceSamples.perp.__doc__ = "Normalised perplexity of the weights of the last ``weigh`` (convergence.py:6-39); no pass over the samples."
+DeviceSamples.ess.__doc__ = "Normalised effective sample size of the weights of the last ``weigh`` (convergence.py:42-72); no pass over the samples."
 
 
 def _check_arguments(samples, weights, latent, mincount, rb):

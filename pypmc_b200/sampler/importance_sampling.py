@@ -8,14 +8,17 @@ What differs from the reference is WHERE the N-loops run, not what they compute:
   (``proposal.multi_evaluate``), and so is the target when it can be evaluated in batch -- a
   :class:`MixtureDensity` (or its bound ``evaluate``), or any object with ``multi_evaluate``.  Other targets are
   arbitrary Python callables and keep the reference's per-sample loop.
-* ``combine_weights`` evaluates every proposal on every run's samples (T^2 launches of K1) and keeps the
-  reference's two formulations (log scale when all weights are positive, linear otherwise).
+* ``combine_weights`` needs log sum_l N_l q_l(y) for every sample of every run.  That sum is itself a mixture (all
+  components of all proposals, weights N_l w_lk), so ONE launch of K1 over all runs' samples yields it, the
+  cross-proposal log-sum-exp included; T more launches give q_t on each run's own samples.  The reference's two
+  formulations are kept (log scale when all weights are positive, linear otherwise).
 """
 from copy import deepcopy as _cp
 
 import numpy as _np
 
 from ..tools._history import History as _History
+from ..density._eval import run_k1 as _run_k1
 from .. import _device as _dev
 
 
@@ -104,6 +107,26 @@ class ImportanceSampler(object):
         _np.exp(target_values - log_q, out=this_weights)
 
 
+def _as_device_vector(v, like):
+    return v if _dev.is_device_tensor(v) else _dev.torch().from_numpy(_np.ascontiguousarray(v, dtype=float)).to(like.device)
+
+
+def _pooled_proposal(proposals, N):
+    """Packed records of ALL components of all ``proposals`` with weights N_l w_lk, or None if the proposals are not
+    mixtures of one CUDA-evaluable kind (all Gauss or all StudentT, same dimension)."""
+    from ..density.mixture import MixtureDensity
+    from .. import _lib
+    if not all(isinstance(p, MixtureDensity) for p in proposals):
+        return None
+    modes = {p._kernel_mode() for p in proposals}
+    if len(modes) != 1 or None in modes or len({p.dim for p in proposals}) != 1 or proposals[0].dim > _lib.MAX_DIM:
+        return None
+    recs = _np.concatenate([_np.stack([c._packed_record() for c in p.components]) for p in proposals])
+    w = _np.concatenate([N[l] * _np.asarray(p.weights, dtype=float) for l, p in enumerate(proposals)])
+    assert (w >= 0.0).all(), "Found negative weight"
+    return _dev.PackedComponents(recs, list(range(len(w))), weights=w), len(w), modes.pop()
+
+
 def combine_weights(samples, weights, proposals):
     """`Deterministic mixture weights` [Cor+12] of importance samples drawn for the same target from different
     proposals (importance_sampling.py:238-371).  Returns a :class:`History` with one run per proposal.
@@ -133,22 +156,38 @@ def combine_weights(samples, weights, proposals):
     log_scale = all((w > 0.0).all() for w in weights)       # all weights positive => log scale (:300-308)
 
     t_ = _dev.torch()
+    y_dev = [_dev.to_device(_np.ascontiguousarray(s_, dtype=float)) for s_ in samples]     # each run uploaded once
+    pooled = _pooled_proposal(proposals, N)
+    if pooled is not None:
+        # sum_l N_l q_l(y) is itself a mixture: all components of all proposals with weights N_l w_lk.  ONE launch of K1
+        # over all runs' samples evaluates its logarithm -- the cross-proposal log-sum-exp (logsumexp2D(q, N),
+        # :333-362) happens inside the kernel -- and one launch per run gives q_t on the run's own samples: T + 1
+        # launches instead of T^2 and no N x T matrix.
+        packed, k_all, mode = pooled
+        y_all = t_.cat(y_dev) if T > 1 else y_dev[0]
+        lse_all = t_.empty(N_total, dtype=t_.float64, device=y_all.device)
+        _run_k1(y_all, packed, k_all, mode, logq=lse_all)
+        lse = t_.split(lse_all, [int(n) for n in N])
+        q_own = [proposals[t].multi_evaluate(y_dev[t]) for t in range(T)]
+    else:
+        # proposals of other kinds (user densities, mixed mixtures): every proposal on every run, reference formulation
+        n_dev = _dev.to_device(N)
+        lse, q_own = [], []
+        for t in range(T):
+            q = t_.stack([_as_device_vector(proposals[l].multi_evaluate(y_dev[t]), y_dev[t]) for l in range(T)], dim=1)
+            m = q.max(dim=1).values
+            lse.append(m + t_.log((n_dev[None, :] * t_.exp(q - m[:, None])).sum(dim=1)))
+            q_own.append(q[:, t])
     for t in range(T):
         out = combined.append(N[t])[:, 0]
-        y = _dev.to_device(_np.ascontiguousarray(samples[t], dtype=float))      # uploaded once, evaluated T times
-        q = t_.stack([proposals[l].multi_evaluate(y) for l in range(T)], dim=1)  # K1: log q_l(y_i^t), [N_t, T] on device
         w_t = _dev.to_device(_np.ascontiguousarray(weights[t], dtype=float))
-        n_dev = _dev.to_device(N)
         if log_scale:
-            # log w = log omega + log q_t + log sum_j N_j - log sum_l N_l q_l(y)   (:333-362); the weighted row-wise
-            # log-sum-exp (logsumexp2D(q, N), _regularize.pyx:57-83) as max + log sum N_l exp(q_l - max)
-            m = q.max(dim=1).values
-            lse = m + t_.log((n_dev[None, :] * t_.exp(q - m[:, None])).sum(dim=1))
-            res = t_.exp(t_.log(w_t) + q[:, t] + float(_np.log(N_total)) - lse)
+            # log w = log omega + log q_t + log sum_j N_j - log sum_l N_l q_l(y)   (:333-362)
+            res = t_.exp(t_.log(w_t) + q_own[t] + float(_np.log(N_total)) - lse[t])
         else:
             # [Cor+12] eq. (3) on linear scale (:314-328)
-            denominator = (n_dev[None, :] * t_.exp(q)).sum(dim=1) / N_total
-            res = t_.exp(q[:, t]) * w_t / denominator
+            denominator = t_.exp(lse[t]) / N_total
+            res = t_.exp(q_own[t]) * w_t / denominator
         out[:] = res.cpu().numpy()
     if log_scale:
         sum_w = combined[:][:, 0].sum()

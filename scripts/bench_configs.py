@@ -2,8 +2,11 @@
 
     python scripts/bench_configs.py [--scale 1.0] [--reps 5] [--cases c2,c3,c4]
 
-The samples are synthetic standard-normal rows (the kernels' run time does not depend on the values); the
-component records are well-conditioned random factors.  Times are CUDA-event medians on the launching stream.
+Samples: ``--data mixture`` (default) draws every row from one of the components, centres ~ N(0, spread^2) with
+spread 3 (the synthetic workload of SURVEY 8d: a sample then has one or two components that matter);
+``--data normal`` gives standard-normal rows under heavily overlapping components (spread 1) -- the worst case for
+K1's log-sum-exp, where every component's term is significant for every sample.  The component records are
+well-conditioned random factors.  Times are CUDA-event medians on the launching stream.
 Flop model: K1 D^2 + 4D per pair, K2 D^2 + 4D + 2 per pair.
 """
 import argparse
@@ -42,7 +45,7 @@ CASES = {
 }
 
 
-def records(K, D, mode, rng):
+def records(K, D, mode, rng, spread=1.0, keep=None):
     recs = []
     for k in range(K):
         t = np.tril(rng.normal(0, 0.3 / np.sqrt(D), size=(D, D))) + np.eye(D)
@@ -55,8 +58,25 @@ def records(K, D, mode, rng):
         else:
             sc[:5] = [-np.log(K), 0.0, D * np.log(2 * np.pi), D / 10.0, 1.0]
         sc[_lib.S_WEIGHT] = 1.0 / K if mode != _lib.MODE_VB else 1.0
-        recs.append(_lib.pack_record(t, rng.normal(0, 1.0, size=D), sc))
+        c = rng.normal(0, spread, size=D)
+        if keep is not None:
+            keep.append((t, c))
+        recs.append(_lib.pack_record(t, c, sc))
     return np.stack(recs)
+
+
+def mixture_rows(N, D, comps, device, seed):
+    """x = c_k + T_k^-1 z for a uniformly drawn component k, in slabs."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    tinv = torch.from_numpy(np.stack([np.linalg.inv(t) for t, _ in comps])).to(device)
+    cen = torch.from_numpy(np.stack([c for _, c in comps])).to(device)
+    x = torch.empty((N, D), dtype=torch.float64, device=device)
+    for s in range(0, N, 1_000_000):
+        m = min(1_000_000, N - s)
+        k = torch.randint(0, len(comps), (m,), device=device, generator=g)
+        z = torch.randn((m, D), dtype=torch.float64, device=device, generator=g)
+        x[s:s + m] = cen[k] + torch.einsum("nij,nj->ni", tinv[k], z)
+    return x
 
 
 def time_ms(fn, reps):
@@ -79,6 +99,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--cases", default="c2_eval,c2_rho,c3_vb,c3_eval,c4_t_eval,c4_t_rho")
     ap.add_argument("--kernels", default="k1,k2")
+    ap.add_argument("--data", default="mixture", choices=["mixture", "normal"])
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     ctx = _lib.Context.get(0)
@@ -89,8 +110,9 @@ def main():
     for name in args.cases.split(","):
         N, K, D, mode, outs = CASES[name]
         N = int(N * args.scale)
-        x = torch.randn((N, D), dtype=torch.float64, device=dev)
-        rec = torch.from_numpy(records(K, D, mode, rng)).to(dev)
+        comps = []
+        rec = torch.from_numpy(records(K, D, mode, rng, spread=3.0 if args.data == "mixture" else 1.0, keep=comps)).to(dev)
+        x = mixture_rows(N, D, comps, dev, seed=7) if args.data == "mixture" else torch.randn((N, D), dtype=torch.float64, device=dev)
         cols = torch.arange(K, dtype=torch.int32, device=dev)
         bufs = {o: torch.empty((N,) if o == "logq" else (N, K), dtype=torch.float64, device=dev) for o in outs}
         sums = torch.zeros(2, dtype=torch.float64, device=dev)
@@ -102,7 +124,7 @@ def main():
         med, best = time_ms(k1, args.reps)
         flops = float(N) * K * (D * D + 4 * D)
         nbytes = 8.0 * N * (D + (1 if "logq" in outs else 0) + K * sum(o != "logq" for o in outs))
-        line = {"case": name, "kernel": "K1", "N": N, "K": K, "D": D, "outputs": list(outs), "ms_median": med, "ms_best": best,
+        line = {"case": name, "kernel": "K1", "data": args.data, "N": N, "K": K, "D": D, "outputs": list(outs), "ms_median": med, "ms_best": best,
                 "tflops": flops / med * 1e-9, "frac_fp64_peak": flops / med * 1e-6 / peak,
                 "alg_GBs": nbytes / med * 1e-6, "pairs_per_s": float(N) * K / med * 1e3}
         print(json.dumps(line), flush=True)
