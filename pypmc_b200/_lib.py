@@ -104,6 +104,29 @@ def pack_record(t_lower: np.ndarray, center: np.ndarray, scalars: np.ndarray) ->
     return rec
 
 
+_PACK_INDEX = {}
+
+
+def pack_records(t_lower: np.ndarray, centers: np.ndarray, scalars: np.ndarray) -> np.ndarray:
+    """``pack_record`` for K components at once in numpy (same layout, csrc/pmc_common.cuh): ``t_lower`` [K, d, d],
+    ``centers`` [K, d], ``scalars`` [K, NUM_SCALARS] -> [K, record_len(d)]."""
+    t = np.asarray(t_lower, dtype=np.float64)
+    k, d = t.shape[0], t.shape[1]
+    idx = _PACK_INDEX.get(d)
+    if idx is None:
+        ii, jj = np.tril_indices(d)
+        pos = 2 * (ii // 2) * (ii // 2 + 1) + 4 * (jj // 2) + 2 * (ii % 2) + (jj % 2)
+        idx = _PACK_INDEX[d] = (ii, jj, pos)
+    ii, jj, pos = idx
+    dp = (d + 1) & ~1
+    nt = (dp // 2) * (dp // 2 + 1) * 2
+    rec = np.zeros((k, record_len(d)))
+    rec[:, pos] = t[:, ii, jj]
+    rec[:, nt:nt + d] = centers
+    rec[:, nt + dp:] = scalars
+    return rec
+
+
 def device_count() -> int:
     return load().pmcb200_device_count()
 

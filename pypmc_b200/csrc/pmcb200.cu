@@ -704,7 +704,7 @@ int pmcb200_mixture_propose(pmcb200_ctx* c, int64_t n, int d, int k, const doubl
   // pageable source: the copy is staged before the call returns, so the caller's array may die at once
   PMC_CUDA_CHECK(cudaMemcpyAsync(c->pws.p, starts_host, size_t(k + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
   ProposeArgs a{n, ldx, d, k, means, chol, dofs, static_cast<const int64_t*>(c->pws.p), seed, index0, x, latent};
-  const size_t smem = sizeof(double) * size_t(K3_THREADS) * (d | 1) + sizeof(int64_t) * size_t(k + 1) + 16;
+  const size_t smem = k3_smem_bytes(d, k);
   PMC_REQUIRE(smem <= 200 * 1024, "mixture_propose: too many components for the shared-memory table");
   static PerDeviceFlag attr_flag;
   bool& attr_set = attr_flag.here();

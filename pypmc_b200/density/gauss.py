@@ -2,7 +2,7 @@
 import numpy as _np
 
 from .base import ProbabilityDensity, LocalDensity
-from ..tools._linalg import chol_inv_det, tri_from_chol, bilinear_sym
+from ..tools._linalg import chol_inv_det, chol_inv_det_batch, tri_from_chol, bilinear_sym
 from .. import _lib
 from .. import _device as _dev
 
@@ -125,3 +125,48 @@ class Gauss(ProbabilityDensity):
         for i in range(N):
             output[i] = self._local_gauss.propose(self.mu, rng)
         return output
+
+
+def batch_update(components, means, covs, dofs=None):
+    """Install new parameters in all ``components`` (all :class:`Gauss`, or all ``StudentT`` with ``dofs``) at once:
+    what ``component.update(mean, cov[, dof])`` does for each of them (gauss.pyx:86-116, student_t.pyx:78-117), with the
+    K factorisations batched and the packed CUDA records of the new parameters formed on the way.  All or nothing:
+    raises ``LinAlgError`` / ``ValueError`` / ``AssertionError`` BEFORE any component is touched if any covariance is
+    unusable -- the caller then runs the reference's per-component loop, which decides component by component."""
+    k = len(components)
+    if k == 0:
+        return
+    means = _np.array(means, dtype=float).reshape(k, -1)
+    covs = _np.array(covs, dtype=float)
+    d = means.shape[1]
+    assert covs.shape == (k, d, d), \
+        "Dimensions of mean (%d) and covariance matrix (%d) do not match!" % (d, covs.shape[-1])
+    low, inv, log_det, t = chol_inv_det_batch(covs)
+    student = dofs is not None
+    scal = _np.zeros((k, _lib.NUM_SCALARS))
+    locals_ = []
+    for i, comp in enumerate(components):
+        local = comp._local_t.__class__.__new__(comp._local_t.__class__) if student else LocalGauss.__new__(LocalGauss)
+        if student:
+            dof = float(dofs[i])
+            assert dof > 0., "Degree of freedom (``dof``) must be greater than zero (got %g)." % dof
+            local.dof, local.symmetric = dof, True
+        local.cholesky_sigma, local.inv_sigma, local.log_det_sigma = low[i], inv[i], float(log_det[i])
+        local.sigma, local.dim = covs[i], d
+        local._compute_norm()
+        locals_.append(local)
+        scal[i, 0] = local.log_normalization
+        scal[i, _lib.S_WEIGHT] = 1.0
+        if student:
+            scal[i, 1:5] = (-.5 * (dof + d), 1. / dof, dof, dof + float(d))
+    records = _lib.pack_records(t, means, scal)
+    for i, comp in enumerate(components):                       # nothing can fail from here on
+        local = locals_[i]
+        if student:
+            comp._local_t, comp.dof = local, local.dof
+            comp._eval_prefactor, comp._inv_dof = -.5 * (local.dof + d), 1. / local.dof
+        else:
+            comp._local_gauss = local
+        comp.mu, comp.dim = means[i].copy(), d
+        comp.inv_sigma, comp.log_det_sigma, comp.sigma = local.inv_sigma, local.log_det_sigma, local.sigma
+        comp._record = records[i]

@@ -16,7 +16,7 @@ import numpy as _np
 from scipy.optimize import brentq as _find_root
 from scipy.special import digamma as _psi
 
-from ..density.gauss import Gauss
+from ..density.gauss import Gauss, batch_update as _batch_update
 from ..density.mixture import MixtureDensity
 from ..density.student_t import StudentT
 from ..density._eval import run_k1
@@ -236,6 +236,17 @@ def _kill_undersampled(density, live, counts, mincount):
 def _apply_update(density, live, alpha, mean, cov, new_dof=None):
     """Install the new parameters; a component whose covariance is not positive definite keeps its old
     parameters and gets weight zero (pmc.pyx:227-244, :713-737).  Returns True if that happened."""
+    live = list(live)
+    try:
+        # all K factorisations in a few batched LAPACK calls; an unusable covariance anywhere raises before anything is
+        # modified and the per-component loop below -- the reference's, with its per-component verdicts -- takes over
+        _batch_update([density.components[k] for k in live], [mean[k] for k in live], [cov[k] for k in live],
+                      None if new_dof is None else [new_dof[k] for k in live])
+        for k in live:
+            density.weights[k] = alpha[k]
+        return False
+    except (_np.linalg.LinAlgError, ValueError, AssertionError):
+        pass
     failed = False
     for k in live:
         comp = density.components[k]

@@ -19,7 +19,7 @@ from scipy.special import gammaln as _gammaln
 from ..density.gauss import Gauss
 from ..density.mixture import MixtureDensity, recover_gaussian_mixture
 from ..density._eval import run_k1
-from ..tools._linalg import chol_inv_det, tri_from_precision
+from ..tools._linalg import chol_inv_det, chol_inv_det_batch, tri_from_precision
 from .. import _device as _dev
 from .. import _lib
 from .. import parallel as _parallel
@@ -207,19 +207,23 @@ class GaussianInference(object):
 
     # ------------------------------------------------------------------------------------------ E / M step
     def _vb_records(self):
-        D = self.dim
-        dlog = D * _np.log(2. * _np.pi)
-        recs = []
-        for k in range(self.K):
-            scalars = _np.zeros(_lib.NUM_SCALARS)
-            scalars[0] = self.expectation_ln_pi[k]
-            scalars[1] = self.expectation_det_ln_lambda[k]
-            scalars[2] = dlog
-            scalars[3] = D / self.beta[k]
-            scalars[4] = self.nu[k]
-            scalars[_lib.S_WEIGHT] = 1.0
-            recs.append(_lib.pack_record(tri_from_precision(self.W[k]), self.m[k], scalars))
-        return _dev.PackedComponents(_np.stack(recs), list(range(self.K)))
+        D, K = self.dim, self.K
+        scalars = _np.zeros((K, _lib.NUM_SCALARS))
+        scalars[:, 0] = self.expectation_ln_pi
+        scalars[:, 1] = self.expectation_det_ln_lambda
+        scalars[:, 2] = D * _np.log(2. * _np.pi)
+        scalars[:, 3] = D / self.beta
+        scalars[:, 4] = self.nu
+        scalars[:, _lib.S_WEIGHT] = 1.0
+        # T_k with T_k^T T_k = W_k: left behind by the M-step that produced W (the inverse Cholesky factor of W^-1),
+        # recomputed only if W was set from outside since
+        cached = getattr(self, "_W_factor", None)
+        if cached is not None and cached[0].shape == self.W.shape and _np.array_equal(cached[0], self.W):
+            t = cached[1]
+        else:
+            t = _np.array([tri_from_precision(self.W[k]) for k in range(K)])
+            self._W_factor = (self.W.copy(), t)
+        return _dev.PackedComponents(_lib.pack_records(t, self.m, scalars), list(range(K)))
 
     def E_step(self):
         """Expectation values and summary statistics (variational.pyx:116-127)."""
@@ -265,14 +269,21 @@ class GaussianInference(object):
         self.alpha = self.alpha0 + self.N_comp
         self.beta = self.beta0 + self.N_comp
         self.m = (self.beta0[:, None] * self.m0 + self.N_comp[:, None] * self.x_mean_comp) / self.beta[:, None]
-        for k in range(self.K):
-            diff = self.x_mean_comp[k] - self.m0[k]
-            cov = _np.outer(diff, diff) * (self.beta0[k] / (self.beta0[k] + self.N_comp[k]))
-            cov += self.S[k]
-            cov *= self.N_comp[k]
-            cov += self.inv_W0[k]
-            self.W[k], log_det = chol_inv_det(cov)[1:]
-            self.log_det_W[k] = -log_det
+        diff = self.x_mean_comp - self.m0
+        cov = (self.beta0 / (self.beta0 + self.N_comp))[:, None, None] * (diff[:, :, None] * diff[:, None, :])
+        cov += self.S
+        cov *= self.N_comp[:, None, None]
+        cov += self.inv_W0
+        try:
+            # K inversions in a few batched LAPACK calls; W_k = cov_k^-1 = T_k^T T_k with T_k the inverse Cholesky factor
+            _, inv, log_det, t = chol_inv_det_batch(cov)
+            self.W = inv
+            self.log_det_W = -log_det
+            self._W_factor = (self.W.copy(), t)
+        except (_np.linalg.LinAlgError, ValueError):
+            for k in range(self.K):                                    # per matrix: the reference's error for the offender
+                self.W[k], log_det = chol_inv_det(cov[k])[1:]
+                self.log_det_W[k] = -log_det
 
     def update(self):
         """One M-step followed by one E-step."""

@@ -51,6 +51,29 @@ def chol_inv_det(m):
     return low, inv, log_det
 
 
+def chol_inv_det_batch(ms):
+    """``chol_inv_det`` for a stack ``ms`` [K, D, D] in a handful of batched LAPACK calls (an update installs K new
+    covariances at once; K separate scipy calls cost 2 ms of host time at K = 32).  Returns ``(L, M^-1, log det M, T)``
+    with ``T = L^-1`` (lower triangular, T^T T = M^-1 -- the factor kernel K1 multiplies with).  Same acceptance
+    conditions as ``chol_inv_det``; raises if ANY matrix fails (``LinAlgError`` / ``ValueError``) without saying which
+    -- callers fall back to the per-matrix routine, whose behaviour is the reference's."""
+    ms = _np.asarray_chkfinite(ms, dtype=float)
+    if ms.ndim != 3 or ms.shape[1] != ms.shape[2]:
+        raise ValueError("expected a stack of square matrices")
+    mt = ms.transpose(0, 2, 1)
+    if not (_np.abs(ms - mt) <= 1e-8 + 1e-5 * _np.abs(mt)).all():
+        raise _np.linalg.LinAlgError("matrix not symmetric")
+    low = _np.linalg.cholesky(ms)                       # LinAlgError when a matrix is not positive definite
+    d = ms.shape[1]
+    t = _np.tril(_np.linalg.solve(low, _np.broadcast_to(_np.eye(d), ms.shape)))
+    inv = t.transpose(0, 2, 1) @ t
+    inv = 0.5 * (inv + inv.transpose(0, 2, 1))
+    log_det = 2.0 * _np.log(_np.diagonal(low, axis1=1, axis2=2)).sum(axis=1)
+    if not _np.isfinite(log_det).all():
+        raise _np.linalg.LinAlgError("Nonpositive eigenvalues lead to invalid determinant")
+    return low, inv, log_det, t
+
+
 def tri_from_chol(low):
     """T = L^-1 (lower triangular), so that ||T y||^2 = y^T (L L^T)^-1 y."""
     t, info = _trtri(low, lower=1)
