@@ -572,6 +572,9 @@ def run_gpu(args):
 
     e2e = dict(host_stream) if world == 1 else dict(iteration)
     e2e["kind"] = "host_stream" if world == 1 else "device_born_iteration"
+    e2e["note"] = ("N = 1: the public call on HOST arrays (what the reference arm evaluates); N > 1: the device-born PMC iteration "
+                   "(host streaming of 2.4 GB per rank cannot scale on one host).  Both records are on every line as "
+                   "e2e_host_stream / e2e_iteration: follow ONE of them across N, not `e2e`, for a scaling figure.")
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
