@@ -25,6 +25,7 @@ CASES = {
     "c2_eval": (10_000_000, 32, 30, _lib.MODE_GAUSS, ("logq",)),
     "c2_rho": (10_000_000, 32, 30, _lib.MODE_GAUSS, ("logq", "resp")),
     "c3_vb": (10_000_000, 64, 20, _lib.MODE_VB, ("resp", "lp")),
+    "c3_vb_r": (10_000_000, 64, 20, _lib.MODE_VB, ("resp",)),          # E-step without materialising log_rho
     "c3_eval": (10_000_000, 64, 20, _lib.MODE_GAUSS, ("logq",)),
     "c4_t_eval": (5_000_000, 16, 40, _lib.MODE_STUDENT_T, ("logq",)),
     "c4_t_rho": (5_000_000, 16, 40, _lib.MODE_STUDENT_T, ("logq", "resp", "aux")),
