@@ -103,17 +103,25 @@ __device__ __forceinline__ double exp_tab(double x, const double* __restrict__ t
   const double v = fma(tj, p, tj);
   return __hiloint2double(__double2hiint(v) + (k >> 8) * 1048576, __double2loint(v));
 }
-// Order-preserving 32-bit key of a double's high word (signed compare of keys == compare of the doubles' upper 32 bits)
-// and its inverse (low word zero).  The log-sum-exp only needs A reference point near the largest log-pdf -- any m gives
+// Order-preserving 32-bit key of a double's high word (signed compare of keys == compare of the doubles' upper 32 bits).
+// The log-sum-exp needs a reference point m at or just below the largest log-pdf of the row -- any m gives
 // m + log sum_k w_k exp(lp_k - m) -- so the maximum is taken over these keys with integer instructions (the FP64 pipe
-// is the one every warp is waiting for) and m is the decoded key: within 2^-20 relative of the true maximum.
+// is the one every warp is waiting for) and m is the SMALLEST double with the winning high word: m <= max_k lp_k <=
+// m + 2^-20 |m|, i.e. the largest term's exponent lies in [0, 2^-20 |m|] (0.0001 at |lp| = 100).
 __device__ __forceinline__ int dkey(double v) {
   const int hi = __double2hiint(v);
   return hi ^ ((hi >> 31) & 0x7fffffff);
 }
-__device__ __forceinline__ double dkey_value(int key) { return __hiloint2double(key ^ ((key >> 31) & 0x7fffffff), 0); }
+__device__ __forceinline__ double dkey_floor(int key) {
+  return __hiloint2double(key ^ ((key >> 31) & 0x7fffffff), key >> 31);   // low word all ones below zero, zero above
+}
 // max(v, 0) on the integer pipe (like fmax: a NaN with the sign bit set also becomes 0)
 __device__ __forceinline__ double clamp0(double v) { return (__double2hiint(v) < 0) ? 0.0 : v; }
+
+// the library exponential, out of line: it is only called in the cold paths (deep tails, the reference's literal rho
+// formula, component groups), and 16-32 inlined copies of it per kernel made the binaries 130-210 KB -- beyond the
+// instruction cache the 16 warps of a CTA, each in a different phase, have to share
+static __device__ __noinline__ double exp_cold(double x) { return exp(x); }
 
 constexpr unsigned kExpSlowHi = 0xC0861800u;                        // high word of -707.0: from there on the library exp runs
 
@@ -156,7 +164,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k1_mma_eval(const MmaArgs ma) {
       scal_s[i] = (k < a.kl) ? a.records[size_t(k) * rl + so + s] : 0.0;
     }
     // Significance thresholds.  A term w_k exp(lp_k - m) below 2^-66 w_min (w_min = the smallest weight) is below
-    // 2^-66 of the sum -- the component that attains the maximum contributes at least w_min exp(-3e-4) -- so dropping
+    // 2^-66 of the sum -- the component that attains the maximum contributes at least w_min (m <= max lp) -- so dropping
     // every such term changes the sum by less than K 2^-66 relative, 1e-18 at K = 64.  With -tau_k = ln(w_min / w_k)
     // - 45.75 a term is kept iff lp_k - m > -tau_k.  For samples that belong to one or two components of a
     // separated mixture (the usual case in D >= 10) this leaves one or two exponentials per sample instead of K.
@@ -425,7 +433,16 @@ __global__ void __launch_bounds__(NW * 32, 1) k1_mma_eval(const MmaArgs ma) {
     for (int nb = 0; nb < NB; ++nb) {
       mkey[nb] = max(mkey[nb], __shfl_xor_sync(0xffffffffu, mkey[nb], 1));
       mkey[nb] = max(mkey[nb], __shfl_xor_sync(0xffffffffu, mkey[nb], 2));
-      mx[nb] = dkey_value(mkey[nb]);                                    // reference point of the log-sum-exp (see dkey)
+      mx[nb] = dkey_floor(mkey[nb]);                                    // reference point of the log-sum-exp (see dkey)
+      if ((mkey[nb] ^ (mkey[nb] >> 31)) >= 0x41B00000) {                 // |m| >= 2^28: m could sit hundreds below the maximum
+        double e = (ma.group > 0) ? m_prev[nb] : mx[nb];                // and exp(lp - m) overflow -- take the exact maximum
+#pragma unroll
+        for (int cb = 0; cb < CB; ++cb) e = fmax(e, fmax(acc[nb][cb][0], acc[nb][cb][1]));
+        const unsigned quad = 0xFu << (lane & ~3);                      // (the four lanes of a row take this branch together)
+        e = fmax(e, __shfl_xor_sync(quad, e, 1));
+        e = fmax(e, __shfl_xor_sync(quad, e, 2));
+        mx[nb] = e;
+      }
     }
 
     // Phase 2: the terms w_k exp(lp - max) of a sample block and their sum over the quad (_regularize.pyx:72-81 up to
@@ -440,7 +457,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k1_mma_eval(const MmaArgs ma) {
     auto quad_sum = [&](int nb, double sum) -> double {
       sum += __shfl_xor_sync(0xffffffffu, sum, 1);
       sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-      if (ma.group > 0) sum = fma(s_prev[nb], exp(m_prev[nb] - mx[nb]), sum);
+      if (ma.group > 0) sum = fma(s_prev[nb], exp_cold(m_prev[nb] - mx[nb]), sum);
       return sum;
     };
     // bit 2 cb + e: the term of component 8 cb + 2 tq + e is significant (d > -tau_k, or a NaN that must propagate)
@@ -497,8 +514,8 @@ __global__ void __launch_bounds__(NW * 32, 1) k1_mma_eval(const MmaArgs ma) {
 #pragma unroll
         for (int cb = 0; cb < CB; ++cb) {
           const double2 w2 = *reinterpret_cast<const double2*>(scl + S_WEIGHT * KP + 8 * cb);
-          if (sig0 & (1u << (2 * cb))) sum += __dmul_rn(w2.x, exp(d[cb][0]));
-          if (sig0 & (2u << (2 * cb))) sum += __dmul_rn(w2.y, exp(d[cb][1]));
+          if (sig0 & (1u << (2 * cb))) sum += __dmul_rn(w2.x, exp_cold(d[cb][0]));
+          if (sig0 & (2u << (2 * cb))) sum += __dmul_rn(w2.y, exp_cold(d[cb][1]));
         }
       }
       return quad_sum(nb, sum);
@@ -520,7 +537,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k1_mma_eval(const MmaArgs ma) {
           const double2 w2 = *reinterpret_cast<const double2*>(scl + S_WEIGHT * KP + 8 * cb);
 #pragma unroll
           for (int e = 0; e < 2; ++e)
-            if (unsigned(__double2hiint(d[cb][e])) >= kExpSlowHi) ex[cb][e] = __dmul_rn(e ? w2.y : w2.x, exp(d[cb][e]));
+            if (unsigned(__double2hiint(d[cb][e])) >= kExpSlowHi) ex[cb][e] = __dmul_rn(e ? w2.y : w2.x, exp_cold(d[cb][e]));
         }
       }
       double sum = 0.0;
@@ -556,7 +573,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k1_mma_eval(const MmaArgs ma) {
         f1 = -ls;
       } else if (ma.rowstat && writer) {                                // for k1_finish
         ma.rowstat[2 * row] = m;
-        ma.rowstat[2 * row + 1] = (a.mode != MODE_VB) ? 1.0 / (exp(lq) + kTiny) : 1.0 / sum;   // pmc.pyx:39-41
+        ma.rowstat[2 * row + 1] = (a.mode != MODE_VB) ? 1.0 / (exp_cold(lq) + kTiny) : 1.0 / sum;   // pmc.pyx:39-41
       }
     };
     if constexpr (!SECOND) {
@@ -589,13 +606,13 @@ __global__ void __launch_bounds__(NW * 32, 1) k1_mma_eval(const MmaArgs ma) {
               ex[cb][e] *= f0;
             }
           if (literal) {
-            const double g0 = 1.0 / (exp(lq) + kTiny);
+            const double g0 = 1.0 / (exp_cold(lq) + kTiny);
 #pragma unroll
             for (int cb = 0; cb < CB; ++cb)
 #pragma unroll
               for (int e = 0; e < 2; ++e)
                 if (acc[nb][cb][e] < -700.0 || literal_row)
-                  ex[cb][e] = exp(acc[nb][cb][e]) * scl[S_WEIGHT * KP + 8 * cb + e] * g0;
+                  ex[cb][e] = exp_cold(acc[nb][cb][e]) * scl[S_WEIGHT * KP + 8 * cb + e] * g0;
           }
           store_pairs(a.resp_out, nb, ex);
         } else {

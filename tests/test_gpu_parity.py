@@ -815,6 +815,12 @@ def test_multi_tile_c2_gauss_vs_oracle(pm, orc):
     from pypmc_b200 import _lib
     K, D, N = 32, 30, 200_003
     means, covs, w, x, sw = _synth(K, D, N, seed=501)
+    # a few samples far outside the mixture (log-pdfs of -1e3 ... -1e8): the significance shortcut of the log-sum-exp
+    # must still find the component(s) that matter, and nothing may overflow
+    direction = np.ones(D) / np.sqrt(D)
+    for i, dist in enumerate((40.0, 300.0, 3e3, 2e4)):
+        x[7 + i] = means[i] + dist * direction
+        x[N - 9 - i] = means[K - 1 - i] - dist * direction
     comps = orc.Components(means, covs)
     mix = create_gaussian_mixture(means, covs, w)
     xd, swd = torch.from_numpy(x).cuda(), torch.from_numpy(sw).cuda()
