@@ -709,7 +709,8 @@ def test_weigh_reuses_the_e_pass(pm):
 @pytest.mark.parametrize("K,D,N,dof", [(32, 30, 5003, None), (64, 20, 3001, None), (16, 40, 2000, 4.0), (14, 9, 1537, None),
                                        (70, 11, 999, 5.0), (35, 13, 700, None), (15, 8, 257, 3.0), (21, 30, 600, None),
                                        (44, 12, 500, 7.0), (52, 10, 400, None), (38, 16, 450, None),
-                                       (64, 30, 1200, None), (32, 40, 900, 6.0), (96, 20, 800, None)])
+                                       (64, 30, 1200, None), (32, 40, 900, 6.0), (96, 20, 800, None),
+                                       (24, 33, 300, None), (16, 8, 100, 4.0), (16, 36, 260, None)])
 def test_k1_matrix_instruction_form(pm, orc, K, D, N, dof):
     """The DMMA form of K1 (k1_mma_eval.cuh, the default for K >= 9, D >= 8 when the component count pads to blocks of
     8 within 20 %; every block count 2..8 is covered, (70, 11) and the last three shapes run in component groups
