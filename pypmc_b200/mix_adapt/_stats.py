@@ -49,6 +49,19 @@ class PacketLayout:
 SHIFT_CONDITION_LIMIT = 1.0e4
 
 
+#: below this many (sample, component) pairs an update is launch-bound anyway and the statistics are taken the
+#: reference's way, in two passes (see :func:`two_pass_suffstats`)
+SMALL_PROBLEM_PAIRS = 200_000
+
+
+def small_problem(n_rows, k):
+    """True if this update takes the two-pass route: a small single-process problem.  With the statistics all-reduce
+    enabled the one-pass route is used on every rank (two passes would need two all-reduces, and ranks hold different
+    row counts but must decide alike)."""
+    from .. import parallel
+    return (not parallel.enabled()) and n_rows * k <= SMALL_PROBLEM_PAIRS
+
+
 def shift_groups(centers, precisions, weights, live, limit=SHIFT_CONDITION_LIMIT):
     """Partition the live components into groups that share one shift vector for kernel K2.
 
@@ -121,6 +134,44 @@ def grouped_suffstats(ctx, ds, lay, packet, groups, rho, gamma, stream):
         ctx.suffstats(ds.x, N, ldx, D, dev.to_device(c, index), rho_g, gamma_g, len(idx), len(idx), ds.w, out, stream)
         rows[cols] = out
         shifts[idx] = c
+    return shifts
+
+
+def two_pass_suffstats(ctx, ds, lay, packet, rho, gamma, live):
+    """The reference's own two-pass statistics (pmc.pyx:196-204, variational.pyx:822-830, 876-890) for small
+    problems: a first launch of K2 about the origin gives sum v and sum v x, hence the new means exactly as the
+    reference forms them (a component whose weighted mean is exactly zero comes out as exactly zero); a second launch
+    per live component accumulates the second moments about THAT mean, so the covariance needs no cancelling
+    correction and is as accurate as the reference's.  K + 1 launches and one host synchronisation in between -- only
+    taken where the whole update costs microseconds (SMALL_PROBLEM_PAIRS); the VB bound then stays monotone to the last
+    bit in the reference's unit tests (variational_test.py:16-37 asserts bound >= old_bound exactly).  Returns the
+    per-component shift array [K, D] the rows of ``packet`` refer to."""
+    from .. import _device as dev
+    K, D, N = lay.K, lay.D, ds.N
+    index = ds.x.device.index
+    ctx = type(ctx).get(index)
+    stream = dev.current_stream_ptr(index)
+    t = dev.torch()
+    ldx = ds.x.stride(0) if N > 1 else D
+    rows = packet[:lay.stats_len].view(K, lay.row)
+    ctx.suffstats(ds.x, N, ldx, D, dev.to_device(np.zeros(D), index), rho, gamma, K, K, ds.w, packet, stream)
+    first = rows.cpu().numpy()
+    shifts = np.zeros((K, D))
+    for k in live:
+        b = first[k, 1]
+        if not (b != 0.0 and np.isfinite(b)):
+            continue                                           # no mass: the zero-shift row stands (regularised later)
+        mean = first[k, 2:2 + D] / b
+        if not np.isfinite(mean).all():
+            continue
+        cols = t.tensor([k], device=rho.device)
+        rho_k = rho.index_select(1, cols).contiguous()
+        gamma_k = None if gamma is None else gamma.index_select(1, cols).contiguous()
+        out = t.empty((1, lay.row), dtype=t.float64, device=rho.device)
+        ctx.suffstats(ds.x, N, ldx, D, dev.to_device(mean, index), rho_k, gamma_k, 1, 1, ds.w, out, stream)
+        rows[k] = out[0]
+        rows[k, 2:2 + D] = 0.0          # the mean IS the first pass's (delta = 0): the second pass only supplies R about it
+        shifts[k] = mean
     return shifts
 
 

@@ -23,7 +23,7 @@ from ..density._eval import run_k1
 from .. import _device as _dev
 from .. import _lib
 from .. import parallel as _parallel
-from ._stats import PacketLayout, moments_from_stats, shift_groups, grouped_suffstats
+from ._stats import PacketLayout, moments_from_stats, shift_groups, grouped_suffstats, small_problem, two_pass_suffstats
 
 logger = logging.getLogger(__name__)
 
@@ -162,6 +162,10 @@ def _e_pass_and_stats(ds, density, live, rb, mode):
         inside = (lat >= 0) & (lat < K)
         packet[lay.off_counts:lay.off_counts + K] = t.bincount(lat[inside], minlength=K)[:K].to(t.float64)
 
+    if live and small_problem(N, K):
+        # small problem: the reference's two passes (means first, second moments about them)
+        shift = two_pass_suffstats(_lib.Context.get(), ds, lay, packet, ds.rho, gamma, live)
+        return lay, lay.unpack(packet.cpu().numpy()), shift
     # shift vector(s) of the raw moments: one for the whole mixture unless components lie > 100 sigma apart
     groups = shift_groups([c.mu for c in density.components], [c.inv_sigma for c in density.components],
                           density.weights, live) if live else []

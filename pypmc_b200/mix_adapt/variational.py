@@ -24,7 +24,7 @@ from ..tools._linalg import chol_inv_det, chol_inv_det_batch, tri_from_precision
 from .. import _device as _dev
 from .. import _lib
 from .. import parallel as _parallel
-from ._stats import PacketLayout, moments_from_stats, shift_groups, grouped_suffstats
+from ._stats import PacketLayout, moments_from_stats, shift_groups, grouped_suffstats, small_problem, two_pass_suffstats
 from .pmc import DeviceSamples
 
 logger = logging.getLogger(__name__)
@@ -250,8 +250,12 @@ class GaussianInference(object):
                sums=packet[lay.off_sum_a:lay.off_sum_a + 2])
         # shift vector(s) of the raw moments: one (alpha-weighted centre) unless components lie > 100 sigma apart;
         # component k is N(m_k, (nu_k W_k)^-1) in expectation
-        groups = shift_groups(self.m, self.nu[:, None, None] * self.W, self.alpha, range(K))
-        shift = grouped_suffstats(_lib.Context.get(), ds, lay, packet, groups, self._r_dev, None, _dev.current_stream_ptr())
+        if small_problem(n, K):
+            # small problem: the reference's two passes (means first, second moments about them)
+            shift = two_pass_suffstats(_lib.Context.get(), ds, lay, packet, self._r_dev, None, range(K))
+        else:
+            groups = shift_groups(self.m, self.nu[:, None, None] * self.W, self.alpha, range(K))
+            shift = grouped_suffstats(_lib.Context.get(), ds, lay, packet, groups, self._r_dev, None, _dev.current_stream_ptr())
         _parallel.allreduce_(packet)
         st = lay.unpack(packet.cpu().numpy())
         self._estep_packed = packed

@@ -22,6 +22,37 @@ from ..density._eval import run_k1 as _run_k1
 from .. import _device as _dev
 
 
+def calculate_expectation(samples, weights, f):
+    r"""sum_n wbar_n f(x_n) with the weights normalised to one (importance_sampling.py:13-44); ``f`` is an arbitrary
+    Python callable, so this is the reference's per-sample loop."""
+    assert len(samples) == len(weights), \
+        "The number of samples (got %i) must equal the number of weights (got %i)." % (len(samples), len(weights))
+    normalization, out = 0., 0.
+    for weight, sample in zip(weights, samples):
+        normalization += weight
+        out += weight * f(sample)
+    return out / normalization
+
+
+def calculate_mean(samples, weights):
+    """Mean of weighted samples (importance_sampling.py:46-60)."""
+    assert len(samples) == len(weights), \
+        "The number of samples (got %i) must equal the number of weights (got %i)." % (len(samples), len(weights))
+    return _np.average(samples, axis=0, weights=weights)
+
+
+def calculate_covariance(samples, weights):
+    """Unbiased covariance of weighted samples (importance_sampling.py:62-84), as one weighted outer-product sum."""
+    assert len(samples) == len(weights), \
+        "The number of samples (got %i) must equal the number of weights (got %i)." % (len(samples), len(weights))
+    samples, weights = _np.asarray(samples, dtype=float), _np.asarray(weights, dtype=float)
+    sum_weights_sq = weights.sum() ** 2
+    sum_sq_weights = (weights ** 2).sum()
+    centred = samples - calculate_mean(samples, weights)
+    second = _np.einsum('n,ni,nj->ij', weights, centred, centred) / weights.sum()
+    return sum_weights_sq / (sum_weights_sq - sum_sq_weights) * second
+
+
 def _batch_form(target):
     """Batch evaluator ``f(samples[N, D]) -> log-values[N]`` of ``target`` if it has one, else None."""
     owner = getattr(target, "__self__", None)

@@ -15,6 +15,15 @@ def regularize(x):
     return x
 
 
+def logsumexp(a, weights):
+    """log(sum_i weights[i] exp(a[i])) as max + log(sum w exp(a - max)) (_regularize.pyx:19-55), 1-d."""
+    a = _np.asarray(a, dtype=float)
+    weights = _np.asarray(weights, dtype=float)
+    assert a.ndim == 1 and a.shape == weights.shape
+    m = a.max() if len(a) else -_np.finfo("d").max
+    return float(_np.log((weights * _np.exp(a - m)).sum()) + m)
+
+
 def logsumexp2D(a, weights):
     """res[n] = max_k a[n, k] + log(sum_k weights[k] exp(a[n, k] - max_k a[n, k])); the maximum runs over ALL columns,
     also those with weight zero (_regularize.pyx:72-81)."""

@@ -662,7 +662,7 @@ def test_weigh_reuses_the_e_pass(pm):
     from pypmc_b200 import _lib
     from pypmc_b200.density.mixture import create_gaussian_mixture, create_t_mixture
     from pypmc_b200.mix_adapt.pmc import gaussian_pmc, student_t_pmc, DeviceSamples
-    K, D, N = 6, 9, 20011
+    K, D, N = 6, 9, 40011                              # (above the two-pass threshold: K2 runs once)
     means, covs, w, _, _ = _synth(K, D, 10, seed=41)
     tmeans = means + 0.1
     for student in (False, True):
