@@ -13,7 +13,8 @@ constexpr size_t kSmemLimit = 227 * 1024;
 // warps 10.7 ms, 16 warps 10.5 ms; C3: (8,4,8) 12.3 ms, (8,2,12) 11.5 ms, (8,2,16) 11.8 ms with spills, (8,1,16)
 // 11.1 ms; profiles/r01f_k1_mma_variants.md).  NB = 2 sample blocks per warp while the accumulators leave room: always
 // for the eval-only instantiation (theta fragments then feed two DMMAs each: K=56, D=20 4.63 vs 4.99 ms), up to CB = 5
-// with the fused second pass, whose second register array would spill beyond that (C3 VB 17.8 vs 13.7 ms).  The
+// with the fused second pass, whose second register array would spill beyond that (C3 VB 17.8 vs 13.7 ms; round 2:
+// (8,2,12) with 168 registers still spills 420 B and measures 13.7 vs 12.5 ms).  The
 // per-sample arithmetic does not depend on NB, so both instantiations give the same log q bit for bit.
 static int nb_for(int cb, bool second) {
   static const char* env = getenv("PMCB200_K1_NB1");              // tuning runs: one sample block for the fused second pass from CB = N on

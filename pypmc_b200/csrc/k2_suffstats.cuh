@@ -83,12 +83,36 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 
 // Producer step for KP <= 32 CV and DP4 <= 64: PR rows per warp pass, every global load of the pass issued before its
 // first use.  Lane l handles columns l + 32 c of V (c < CV) and of Y (c < 2).
-template <int PR, int CV>
+// TR (the matrix-instruction consumers): the stage is TRANSPOSED in blocks of 8 samples, V [TN/8][KW][8] | Y [TN/8][DP4][8],
+// so that a consumer lane fetches the operands of two 4-sample steps (samples 2 tq, 2 tq + 1 of the block) with ONE
+// LDS.128 -- an LDS instruction of either width costs the sub-partition about 2.8 clk of FP64 issue
+// (scripts/ubench/k2_feed.cu), and halving their number is worth 5 (C2) to 8 (C4) points of the pipe.
+// Inside a column's 64 bytes the four 16-byte sample pairs are XOR-swizzled with bits 1..2 of the column index: the
+// producers (lane = column, one pair per store) then hit eight different 16-byte bank groups per quarter-warp, and a
+// consumer quarter-warp (two columns x four pairs) still covers 128 contiguous bytes.
+__device__ __forceinline__ int k2_swz(int col, int pair) { return pair ^ ((col >> 1) & 3); }
+template <bool TR, int PR>
+__device__ __forceinline__ void k2_store_rows(double* base, int rb, int col, int ncols, const double (&v)[PR]) {
+  if constexpr (TR) {
+    static_assert(PR == 2 || PR == 4, "rows of a pass share one 8-sample block");
+    double* blk = base + (rb >> 3) * (ncols * 8) + col * 8;
+#pragma unroll
+    for (int u = 0; u < PR; u += 2)
+      *reinterpret_cast<double2*>(blk + 2 * k2_swz(col, ((rb & 7) + u) >> 1)) = make_double2(v[u], v[u + 1]);
+  } else {
+    double* dst = base + rb * ncols + col;
+#pragma unroll
+    for (int u = 0; u < PR; ++u) dst[u * ncols] = v[u];
+  }
+}
+
+template <int PR, int CV, bool TR>
 __device__ __forceinline__ void k2_fill_stage(const StatsArgs& a, double* Vs, double* Ys, const double* shift_s,
                                               int64_t row0, int rows, int pw, int lane, bool has_g, int KP,
                                               const double* __restrict__ rho, const double* __restrict__ gamma, int kvalid) {
   // rho / gamma point at this CTA's first staged column; kvalid of the KP staged columns hold components
-  const int D = a.d, DP4 = a.DP4, TN = a.tn, VS = a.VS, YS = a.YS;
+  const int D = a.d, DP4 = a.DP4, TN = a.tn, VS = a.VS, YS = a.YS;   // TR: VS / YS = columns per block
+  const bool has_w = a.sw != nullptr;
   for (int rb = pw * PR; rb < TN; rb += 4 * PR) {
     double w[PR], rv[PR][CV], gv[PR][CV], xv[PR][2];
 #pragma unroll
@@ -109,13 +133,20 @@ __device__ __forceinline__ void k2_fill_stage(const StatsArgs& a, double* Vs, do
         xv[u][c] = (rin && kk < D) ? __ldg(a.x + row * a.ldx + kk) : 0.0;
       }
     }
+    // (TN is a multiple of 8 and rb of PR, so the PR rows of a pass lie inside the stage and inside one 8-sample block)
 #pragma unroll
     for (int c = 0; c < CV; ++c) {
       const int kk = lane + 32 * c;                         // column of V handled by this lane
       if (kk < KP) {
+        double v[PR];
 #pragma unroll
-        for (int u = 0; u < PR; ++u)
-          if (rb + u < TN) Vs[(rb + u) * VS + kk] = rv[u][c] * w[u] * gv[u][c];
+        for (int u = 0; u < PR; ++u) {
+          // (the producers' FP64 instructions queue behind the consumers' DMMAs: none that is not needed)
+          v[u] = rv[u][c];
+          if (has_w) v[u] *= w[u];
+          if (has_g) v[u] *= gv[u][c];
+        }
+        k2_store_rows<TR, PR>(Vs, rb, kk, VS, v);
       }
     }
 #pragma unroll
@@ -123,12 +154,13 @@ __device__ __forceinline__ void k2_fill_stage(const StatsArgs& a, double* Vs, do
       const int kk = lane + 32 * c;                         // column of Y handled by this lane
       if (kk < DP4) {
         const double sh = shift_s[kk];
+        double y[PR];
 #pragma unroll
         for (int u = 0; u < PR; ++u) {
-          double y = 0.0;
-          if (rb + u < rows) y = (kk < D) ? (xv[u][c] - sh) : ((kk == D) ? 1.0 : 0.0);
-          if (rb + u < TN) Ys[(rb + u) * YS + kk] = y;
+          y[u] = 0.0;
+          if (rb + u < rows) y[u] = (kk < D) ? (xv[u][c] - sh) : ((kk == D) ? 1.0 : 0.0);
         }
+        k2_store_rows<TR, PR>(Ys, rb, kk, YS, y);
       }
     }
   }
@@ -147,6 +179,7 @@ __device__ __forceinline__ void k2_fill_stage(const StatsArgs& a, double* Vs, do
 template <int CB, int FB>
 __global__ void __launch_bounds__(K2_THREADS, 1) k2_suffstats(const StatsArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr bool TR = CB > 0;                       // stage layout: transposed 8-sample blocks for the matrix-instruction form
   const int tid = threadIdx.x;
   const int D = a.d, KP = a.KP, DP4 = a.DP4, TN = a.tn, VS = a.VS, YS = a.YS;
   const bool has_g = a.gamma != nullptr;
@@ -187,14 +220,31 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_suffstats(const StatsArgs a)
       double* Ys = Vs + TN * VS;
       const int64_t row0 = tile * TN;
       const int rows = int((a.n - row0 < TN) ? (a.n - row0) : TN);
+      // The producers are latency-bound (a pass = issue every load of 4 rows, wait, store): pull the rows of this CTA's
+      // NEXT tile into L2 now, so that the loads of the next stage cost an L2 round trip instead of an HBM one.  With few
+      // FMAs per staged byte (K = 40, D = 20: consumers 20 % of their time on `full`) that is what bounds the kernel.
+      {
+        const int64_t nrow = row0 + int64_t(gridDim.x) * TN + (tid - K2_CONSUMERS);
+        if (tid - K2_CONSUMERS < TN && nrow < a.n) {
+          const char* pr = reinterpret_cast<const char*>(rho_c + nrow * a.ld_rho);
+          for (int b = 0; b < kvalid * 8; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + b));
+          if (has_g) {
+            const char* pg = reinterpret_cast<const char*>(gamma_c + nrow * a.ld_rho);
+            for (int b = 0; b < kvalid * 8; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pg + b));
+          }
+          const char* px = reinterpret_cast<const char*>(a.x + nrow * a.ldx);
+          for (int b = 0; b < D * 8; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(px + b));
+          if (a.sw && ((tid - K2_CONSUMERS) & 15) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.sw + nrow));
+        }
+      }
       if (KW <= 64 && DP4 <= 64) {
         // common sizes: every global load of a 4-row step is issued before the first use (about 20 in flight per
         // thread), so a step costs one memory latency instead of one per column block
-        k2_fill_stage<K2_PR, 2>(a, Vs, Ys, shift_s, row0, rows, pw, lane, has_g, KW, rho_c, gamma_c, kvalid);
+        k2_fill_stage<K2_PR, 2, TR>(a, Vs, Ys, shift_s, row0, rows, pw, lane, has_g, KW, rho_c, gamma_c, kvalid);
       } else if (KW <= 128 && DP4 <= 64) {
         // 65..128 components: the same with two rows in flight and four column blocks per lane (the register budget of
         // the producer warps, 88, holds 2 x (4 rho + 4 gamma + 2 x) values)
-        k2_fill_stage<2, 4>(a, Vs, Ys, shift_s, row0, rows, pw, lane, has_g, KW, rho_c, gamma_c, kvalid);
+        k2_fill_stage<2, 4, TR>(a, Vs, Ys, shift_s, row0, rows, pw, lane, has_g, KW, rho_c, gamma_c, kvalid);
       } else {
         for (int rb = pw * K2_PR; rb < TN; rb += 4 * K2_PR) {       // K2_PR rows in flight per warp
           double w[K2_PR];
@@ -208,9 +258,14 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_suffstats(const StatsArgs a)
               rv[u] = in ? __ldg(rho_c + (row0 + rb + u) * a.ld_rho + kk) : 0.0;
               gv[u] = (in && has_g) ? __ldg(gamma_c + (row0 + rb + u) * a.ld_rho + kk) : 1.0;
             }
+            double v[K2_PR];
   #pragma unroll
-            for (int u = 0; u < K2_PR; ++u)
-              if (rb + u < TN) Vs[(rb + u) * VS + kk] = rv[u] * w[u] * gv[u];
+            for (int u = 0; u < K2_PR; ++u) {
+              v[u] = rv[u];
+              if (a.sw) v[u] *= w[u];
+              if (has_g) v[u] *= gv[u];
+            }
+            k2_store_rows<TR, K2_PR>(Vs, rb, kk, VS, v);
           }
           for (int jj = lane; jj < DP4; jj += 32) {
             double xv[K2_PR];
@@ -218,12 +273,13 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_suffstats(const StatsArgs a)
             for (int u = 0; u < K2_PR; ++u)
               xv[u] = (rb + u < rows && jj < D) ? __ldg(a.x + (row0 + rb + u) * a.ldx + jj) : 0.0;
             const double sh = shift_s[jj];
+            double y[K2_PR];
   #pragma unroll
             for (int u = 0; u < K2_PR; ++u) {
-              double y = 0.0;
-              if (rb + u < rows) y = (jj < D) ? (xv[u] - sh) : ((jj == D) ? 1.0 : 0.0);
-              if (rb + u < TN) Ys[(rb + u) * YS + jj] = y;
+              y[u] = 0.0;
+              if (rb + u < rows) y[u] = (jj < D) ? (xv[u] - sh) : ((jj == D) ? 1.0 : 0.0);
             }
+            k2_store_rows<TR, K2_PR>(Ys, rb, jj, YS, y);
           }
         }
       }
@@ -258,7 +314,8 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_suffstats(const StatsArgs a)
         while (r * (r + 1) / 2 > t) --r;
         oi = r; oj = t - r * (r + 1) / 2;
       }
-      off_i[fb] = oi; off_j[fb] = oj;
+      off_i[fb] = oi * 64 + 16 * k2_swz(oi, tq);          // byte offsets inside an 8-sample block: column, swizzled pair tq
+      off_j[fb] = oj * 64 + 16 * k2_swz(oj, tq);
     }
     // staged column of each of this warp's component blocks: with `chunked` the CTA staged only its own columns (from
     // 0), otherwise all of them; blocks beyond KP/8 (cb_total not a multiple of CB) re-read column block 0 and are
@@ -266,7 +323,10 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_suffstats(const StatsArgs a)
     int cb_off[CB];
 #pragma unroll
     for (int cb = 0; cb < CB; ++cb)
-      cb_off[cb] = (cb_first + cb < cb_total) ? (a.chunked ? 0 : cb_first * 8) + cb * 8 : 0;
+    {
+      const int col = ((cb_first + cb < cb_total) ? (a.chunked ? 0 : cb_first * 8) + cb * 8 : 0) + g;
+      cb_off[cb] = col * 64 + 16 * k2_swz(col, tq);        // bytes
+    }
     double acc[CB][FB][2];
 #pragma unroll
     for (int cb = 0; cb < CB; ++cb)
@@ -281,23 +341,37 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_suffstats(const StatsArgs a)
       const double* Ys = Vs + TN * VS;
       if (nfb_w > 0) {
         // no branch inside the step: feature blocks beyond the warp's share multiply the zero column, so every
-        // load of a step can be issued before its first DMMA and the 32 DMMAs go back to back
-#pragma unroll 2
-        for (int n0 = 0; n0 < TN; n0 += 4) {
-          const double* vrow = Vs + (n0 + tq) * VS + g;
-          const double* yrow = Ys + (n0 + tq) * YS;
-          double av[CB], bv[FB];
+        // load of a step can be issued before its first DMMA and the DMMAs go back to back.  One pass = an 8-sample
+        // block = two 4-sample steps (samples 2 tq and 2 tq + 1 of the block are the k index of the first / second
+        // step): CB + 2 FB LDS.128, 2 FB DMUL, 2 CB FB DMMA.
+        const char* vblk = reinterpret_cast<const char*>(Vs);
+        const char* yblk = reinterpret_cast<const char*>(Ys);
+        for (int n0 = 0; n0 < TN; n0 += 8, vblk += VS * 64, yblk += YS * 64) {
+          double2 av[CB];
+          double b0[FB], b1[FB];
 #pragma unroll
-          for (int cb = 0; cb < CB; ++cb) av[cb] = vrow[cb_off[cb]];
+          for (int cb = 0; cb < CB; ++cb) av[cb] = *reinterpret_cast<const double2*>(vblk + cb_off[cb]);
 #pragma unroll
-          for (int fb = 0; fb < FB; ++fb) bv[fb] = yrow[off_i[fb]] * yrow[off_j[fb]];
+          for (int fb = 0; fb < FB; ++fb) {
+            const double2 yi = *reinterpret_cast<const double2*>(yblk + off_i[fb]);
+            const double2 yj = *reinterpret_cast<const double2*>(yblk + off_j[fb]);
+            b0[fb] = yi.x * yj.x;
+            b1[fb] = yi.y * yj.y;
+          }
 #pragma unroll
           for (int fb = 0; fb < FB; ++fb)
 #pragma unroll
             for (int cb = 0; cb < CB; ++cb)
               asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                            : "+d"(acc[cb][fb][0]), "+d"(acc[cb][fb][1])
-                           : "d"(av[cb]), "d"(bv[fb]));
+                           : "d"(av[cb].x), "d"(b0[fb]));
+#pragma unroll
+          for (int fb = 0; fb < FB; ++fb)
+#pragma unroll
+            for (int cb = 0; cb < CB; ++cb)
+              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                           : "+d"(acc[cb][fb][0]), "+d"(acc[cb][fb][1])
+                           : "d"(av[cb].y), "d"(b1[fb]));
         }
       }
       mbar_arrive(&empty[s]);                                   // the producer may refill this stage
@@ -404,27 +478,63 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_suffstats(const StatsArgs a)
 }
 
 #ifndef PMC_K2_TEMPLATE_ONLY   // (k2_inst.cu instantiates more tile shapes of the template above and needs only that)
+}  // namespace pmc
+#include "k1_exp_table.cuh"
+namespace pmc {
 // ---------------------------------------------------------------------------------------------
 // Column sums that go with gamma (Student-t): A_k = sum_n w_n rho_nk and L_k = sum_n w_n rho_nk ln(gamma_nk)
 // (the N-sized part of the dof condition, pmc.pyx:654-691).  A streaming pass of its own: in the producer warps of
 // k2_suffstats the logarithm cost 2 ms of 8 at C4 (4 warps per SM, latency-bound); here every SM runs 8 full CTAs.
 // Thread t owns column t % kc and rows t / kc, t / kc + 256 / kc, ...; per-CTA partials, summed in CTA order.
 // ---------------------------------------------------------------------------------------------
+// ln(x) for any positive normal x (else the library function): x = 2^e m, m in [1, 2), c_j = 1 + (j + 1/2)/128 for the top
+// seven mantissa bits, r = m / c_j - 1, ln x = e ln2 + ln c_j + (r - r^2/2 + ... - r^6/6) -- the table logarithm of K1's
+// Student-t epilogue (k1_mma_eval.cuh: log_tab) with the exponent term formed by two FMAs, so arguments below 1 (gamma
+// < 1 for samples beyond the component's bulk) need no table entry.  10 FP64 instructions; absolute error <= 2e-16 (1 + |ln x|).
+__device__ __forceinline__ double k2_log_pos(double x, const double* __restrict__ tab /* [1/c_j | ln c_j] */) {
+  const int hi = __double2hiint(x);
+  if (unsigned(hi) - 0x00100000u >= 0x7fe00000u) return log(x);        // zero, subnormal, negative, inf, nan
+  const int j = (hi >> 13) & 127;
+  const double e = double((hi >> 20) - 1023);
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+  const double r = fma(m, tab[j], -1.0);
+  double u = fma(r, -1.66666666666666657e-01, 2.00000000000000011e-01);
+  u = fma(r, u, -0.25);
+  u = fma(r, u, 3.33333333333333315e-01);
+  u = fma(r, u, -0.5);
+  const double p = fma(r * r, u, r);
+  return fma(e, 0x1.62e42fefa38p-1, (p + tab[128 + j]) + e * 0x1.ef35793c7673p-45);   // ln 2 = hi (43 bits: e hi exact) + lo
+}
+
 __global__ void __launch_bounds__(256) k2_colsums(const double* __restrict__ rho, const double* __restrict__ gamma,
                                                   const double* __restrict__ sw, int64_t n, int k, int ld_rho, int kc,
                                                   double* __restrict__ partial /* [grid][2][k] */) {
   __shared__ double red[2][256];
+  __shared__ double ltab[256];
   const int tid = threadIdx.x, rows_per_pass = 256 / kc, r_off = tid / kc;
+  if (tid < 128) { ltab[tid] = kLogInvC[tid]; ltab[128 + tid] = kLogC[tid]; }
+  __syncthreads();
+  constexpr int U = 4;                                               // rows in flight per thread
   for (int k0 = 0; k0 < k; k0 += kc) {
     const int kk = k0 + tid % kc;
     double sa = 0.0, sl = 0.0;
     if (kk < k) {
-      for (int64_t r = int64_t(blockIdx.x) * rows_per_pass + r_off; r < n; r += int64_t(gridDim.x) * rows_per_pass) {
-        double v = __ldg(rho + r * ld_rho + kk);
-        if (sw) v *= __ldg(sw + r);
-        const double gm = __ldg(gamma + r * ld_rho + kk);
-        sa += v;
-        sl += (v != 0.0) ? v * log(gm) : 0.0;
+      const int64_t stride = int64_t(gridDim.x) * rows_per_pass;
+      for (int64_t r = int64_t(blockIdx.x) * rows_per_pass + r_off; r < n; r += U * stride) {
+        double v[U], gm[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int64_t ru = r + u * stride;
+          const bool in = ru < n;
+          v[u] = in ? __ldg(rho + ru * ld_rho + kk) : 0.0;
+          gm[u] = in ? __ldg(gamma + ru * ld_rho + kk) : 1.0;
+          if (sw && in) v[u] *= __ldg(sw + ru);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {                                 // (row order as before: r, r + stride, ...)
+          sa += v[u];
+          sl += (v[u] != 0.0) ? v[u] * k2_log_pos(gm[u], ltab) : 0.0;
+        }
       }
     }
     red[0][tid] = sa;
@@ -440,22 +550,34 @@ __global__ void __launch_bounds__(256) k2_colsums(const double* __restrict__ rho
   }
 }
 
-// out[k][0] = A_k, out[k][F+1] = L_k from the per-CTA partials (CTA order); L_k = 0 without gamma
-__global__ void k2_colsums_final(const double* __restrict__ partial, int nblocks, int k, int ldp, int F, int has_gamma,
-                                 double* __restrict__ out) {
-  const int kk = blockIdx.x * blockDim.x + threadIdx.x;
+// out[k][0] = A_k, out[k][F+1] = L_k from the per-CTA partials; L_k = 0 without gamma.  One CTA per component: thread t
+// adds the partials of CTAs t, t + 256, ... in ascending order, then a fixed tree over the threads -- reproducible, and
+// microseconds where one thread per component walking all ~1200 partials took 0.2 ms.
+__global__ void __launch_bounds__(256) k2_colsums_final(const double* __restrict__ partial, int nblocks, int k, int ldp,
+                                                        int F, int has_gamma, double* __restrict__ out) {
+  __shared__ double red[2][256];
+  const int kk = blockIdx.x, tid = threadIdx.x;
   if (kk >= k) return;
   if (!has_gamma) {
-    out[size_t(kk) * ldp + F + 1] = 0.0;
+    if (tid == 0) out[size_t(kk) * ldp + F + 1] = 0.0;
     return;
   }
   double a0 = 0.0, l0 = 0.0;
-  for (int b = 0; b < nblocks; ++b) {
+  for (int b = tid; b < nblocks; b += 256) {
     a0 += partial[(size_t(b) * 2 + 0) * k + kk];
     l0 += partial[(size_t(b) * 2 + 1) * k + kk];
   }
-  out[size_t(kk) * ldp] = a0;
-  out[size_t(kk) * ldp + F + 1] = l0;
+  red[0][tid] = a0;
+  red[1][tid] = l0;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (tid < o) { red[0][tid] += red[0][tid + o]; red[1][tid] += red[1][tid + o]; }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    out[size_t(kk) * ldp] = red[0][0];
+    out[size_t(kk) * ldp + F + 1] = red[1][0];
+  }
 }
 
 // out[e] = sum_b partial[b][e], b ascending (fixed order)

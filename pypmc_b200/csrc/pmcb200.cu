@@ -452,8 +452,8 @@ int pmcb200_suffstats(pmcb200_ctx* c, const double* x, int64_t n, int64_t ldx, i
     a.chunked = (cchunks > 1) ? 1 : 0;                   // several CTAs share the component blocks: each stages its own
     a.cb8 = cbw * 8;
     a.kchunk = ((a.cb8 + 15) / 16) * 16;
-    a.VS = (a.chunked ? a.kchunk : a.KP) + 4;            // row strides = 4 (mod 16) doubles: the 8 x 4 fragment loads of a
-    a.YS = ((a.DP4 + 11) / 16) * 16 + 4;                 // half-warp then touch 16 different 8-byte banks
+    a.VS = a.chunked ? a.kchunk : a.KP;                  // transposed stage, blocks of 8 samples: V [tn/8][VS][8] | Y [tn/8][YS][8]
+    a.YS = a.DP4;                                        // (64 bytes per column: neighbouring columns fall in opposite bank halves)
   } else {
     a.nFB = 0;
     a.fchunks = 1;
@@ -514,7 +514,7 @@ int pmcb200_suffstats(pmcb200_ctx* c, const double* x, int64_t n, int64_t ldx, i
     PMC_CUDA_CHECK(cudaGetLastError());
     c->launches++;
   }
-  k2_colsums_final<<<unsigned((k + 127) / 128), 128, 0, st>>>(static_cast<const double*>(c->cws.p), cgrid, k, F + 2, F,
+  k2_colsums_final<<<unsigned(k), 256, 0, st>>>(static_cast<const double*>(c->cws.p), cgrid, k, F + 2, F,
                                                                gamma ? 1 : 0, out);
   PMC_CUDA_CHECK(cudaGetLastError());
   c->launches++;
