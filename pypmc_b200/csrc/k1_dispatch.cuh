@@ -18,7 +18,7 @@ struct K1Launch {
     static constexpr int kMaxGroups = 16;
     int groups = 0;                       // component groups, one k1_mma_eval launch each
     int k0[kMaxGroups] = {}, count[kMaxGroups] = {}, cb[kMaxGroups] = {};   // first component, components, blocks of 8
-    size_t theta_off[kMaxGroups] = {};    // offset (doubles) of the group's theta [steps][8 cb][4]
+    size_t theta_off[kMaxGroups] = {};    // offset (doubles) of the group's theta [steps / 2][8 cb][4][2]
     size_t theta_len = 0;
     int steps = 0;
   } mma;

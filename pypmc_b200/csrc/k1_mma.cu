@@ -38,7 +38,7 @@ bool k1_mma_plan(int kl, int d, K1Launch::MmaPlan* plan) {
   if (groups > K1Launch::MmaPlan::kMaxGroups || slots * 100 > kl * 120) return false;
   if (groups > 1 && cbmax < 4 && d < 33) return false;
   plan->groups = groups;
-  plan->steps = (k1m_features(d) + 3) / 4;
+  plan->steps = k1m_steps(d);
   size_t off = 0;
   for (int g = 0; g < groups; ++g) {
     plan->k0[g] = g * 8 * cbmax;

@@ -53,10 +53,10 @@ constexpr int K1M_LOGTAB = 128 + 128 + 64;   // 1 / c_j, ln c_j (j < 128), e ln 
 
 struct MmaArgs {
   EvalArgs e;             // e.records = derived records ([T | -b | scalars]); only the scalars are read here
-  const double* theta;    // [steps][KP][4]
+  const double* theta;    // [steps / 2][KP][4][2]  (k1m_theta_index)
   const double* shift;    // [d]
   const int* flag;        // flag[0] != 0: exact-difference form runs; else flag[1] != 0: this form runs; else k1_fast_eval
-  int steps;              // feature quads = ceil(F / 4)
+  int steps;              // feature quads = ceil(F / 4) rounded up to even (k1m_steps)
   int KP;                 // components (of this group) padded to 8 CB
   // Component groups: when theta of all components does not fit shared memory, the components are evaluated in
   // `ngroups` launches of at most KP each (e.records / e.cols / e.kl / theta describe THIS group).  The running
@@ -70,8 +70,15 @@ __host__ __device__ inline int k1m_features(int d) { return 1 + d + d * (d + 1) 
 // slots per column of a warp's slice: 8 NB samples + 4 of padding.  The column stride is then 20 (NB = 2) or 12
 // (NB = 1) doubles, == 4 and 12 (mod 16): the x_j loads of a quad -- 4 columns x 8 NB samples -- touch every bank once.
 __host__ __device__ constexpr int k1m_col_stride(int NB) { return 8 * NB + 4; }
+// feature quads, rounded up to an even count: the loop takes them in PAIRS (see the mapping note above); theta is stored
+// [pair][component][feature in quad][quad of the pair], so that a lane's fragments of both quads are one 16-byte load
+__host__ __device__ inline int k1m_steps(int d) { return ((k1m_features(d) + 3) / 4 + 1) & ~1; }
+__host__ __device__ inline size_t k1m_theta_index(int f, int KP, int slot) {
+  const int s = f >> 2;
+  return (size_t(s >> 1) * KP + slot) * 8 + (f & 3) * 2 + (s & 1);
+}
 inline size_t k1m_smem_bytes(int d, int KP, int NB, int NW) {
-  const int steps = (k1m_features(d) + 3) / 4, dp = (d + 1) & ~1;
+  const int steps = k1m_steps(d), dp = (d + 1) & ~1;
   return sizeof(double) * (size_t(steps) * KP * 4 + size_t(KP) * K1M_SCAL + dp + K1M_EXPTAB + K1M_LOGTAB +
                            size_t(NW) * (d + 2) * k1m_col_stride(NB)) +
          sizeof(int) * size_t(steps) * 4 + 16;
@@ -166,18 +173,18 @@ __global__ void __launch_bounds__(NW * 32, 1) k1_mma_eval(const MmaArgs ma) {
   const EvalArgs& a = ma.e;
   if (ma.flag[0] != 0 || ma.flag[1] == 0) return;
   constexpr int RW = 8 * NB, TS = RW * NW, KP = 8 * CB, RS = k1m_col_stride(NB);
-  constexpr int UNR = (CB * NB <= 4) ? 4 : (CB * NB >= 12) ? 1 : 2;   // feature quads per loop body (about 16 DMMAs)
+  constexpr int UNR = (CB * NB <= 4) ? 2 : 1;                          // pairs of feature quads per loop body (16 DMMAs or more)
   const int D = a.d, steps = ma.steps, dp = (D + 1) & ~1;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  double* theta_s = reinterpret_cast<double*>(smem_raw);               // [steps][KP][4]
+  double* theta_s = reinterpret_cast<double*>(smem_raw);               // [steps / 2][KP][4][2]
   double* scal_s = theta_s + size_t(steps) * KP * 4;                   // [K1M_SCAL][KP]
   double* cs = scal_s + KP * K1M_SCAL;                                 // [dp] shift
   double* etab = cs + dp;                                              // [256] 2^(j/256)
   double* ltab = etab + K1M_EXPTAB;                                    // [128 | 128 | 64] log_tab()
   double* y_all = ltab + K1M_LOGTAB;                                   // [NW][D + 2][RS]
   const int slice = (D + 2) * RS;
-  int* tab = reinterpret_cast<int*>(y_all + size_t(NW) * slice);      // [steps * 4] byte offsets (column i | column j << 16)
+  int* tab = reinterpret_cast<int*>(y_all + size_t(NW) * slice);      // [steps / 2][4][2] byte offsets (column i | column j << 16)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, tq = lane & 3;
@@ -223,7 +230,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k1_mma_eval(const MmaArgs ma) {
       if (f == 0) { oi = D; oj = D; }
       else if (f <= D) { oi = f - 1; oj = D; }
       else if (f < F) tri_index(f - 1 - D, oi, oj);
-      tab[f] = (oi * RS * 8) | ((oj * RS * 8) << 16);
+      tab[(((f >> 3) * 4) + (f & 3)) * 2 + ((f >> 2) & 1)] = (oi * RS * 8) | ((oj * RS * 8) << 16);
     }
     for (int i = tid; i < NW * slice; i += blockDim.x) y_all[i] = ((i % slice) / RS == D) ? 1.0 : 0.0;
   }
@@ -243,8 +250,8 @@ __global__ void __launch_bounds__(NW * 32, 1) k1_mma_eval(const MmaArgs ma) {
 
   double* yw = y_all + size_t(warp) * slice;
   const char* ylane = reinterpret_cast<const char*>(yw + g * NB);      // this lane's sample slot(s) in column 0
-  const double* thl = theta_s + g * 4 + tq;                            // theta[s][8 cb + g][tq]
-  const int* tabl = tab + tq;
+  const double2* thl = reinterpret_cast<const double2*>(theta_s) + g * 4 + tq;   // theta[pair][8 cb + g][tq] = (quad 2p, quad 2p + 1)
+  const int2* tabl = reinterpret_cast<const int2*>(tab) + tq;
   const double* scl = scal_s + 2 * tq;                                 // scalars of components 8 cb + 2 tq + {0, 1}
 
   const int64_t num_tiles = (a.n + TS - 1) / TS;
@@ -317,39 +324,61 @@ __global__ void __launch_bounds__(NW * 32, 1) k1_mma_eval(const MmaArgs ma) {
 #pragma unroll
       for (int cb = 0; cb < CB; ++cb) { acc[nb][cb][0] = 0.0; acc[nb][cb][1] = 0.0; }
 
-    // ---- q = phi . theta over the feature quads; the operands of quad s + 1 are fetched before the DMMAs of quad s ----
-    double th_n[CB], yi_n[NB], yj_n[NB];
-    auto fetch = [&](int s) {
-      const unsigned t = unsigned(tabl[4 * s]);
-      const char* pi = ylane + (t & 0xffffu);
-      const char* pj = ylane + (t >> 16);
-#pragma unroll
-      for (int cb = 0; cb < CB; ++cb) th_n[cb] = thl[(s * KP + cb * 8) * 4];
+    // ---- q = phi . theta over the feature quads, two quads per pass (round 2, scripts/ubench/k1_feed.cu: an LDS
+    // instruction of either width costs the sub-partition's DMMA issue about the same, so theta travels as ONE LDS.128 per
+    // component block and pair of quads, the table word of both quads as one LDS.64).  The y operands of the next pair
+    // are fetched before the DMMAs of this one; a theta fragment is reloaded in place right after its last DMMA of the
+    // pair -- component blocks go in groups of G, quad 0 then quad 1 of the group, so the two DMMAs on one accumulator
+    // stay G NB instructions apart and no second fragment buffer is needed (bare loop at C2 89.8 -> 93.9 % of the pipe).
+    // Every accumulator still sees the quads in ascending order: same bits as the quad-at-a-time loop.
+    const int pairs = steps >> 1;
+    double yi_n[2][NB], yj_n[2][NB];
+    double2 th[CB];
+    auto ld_y = [&](unsigned off, double (&v)[NB]) {
       if constexpr (NB == 2) {
-        const double2 vi = *reinterpret_cast<const double2*>(pi), vj = *reinterpret_cast<const double2*>(pj);
-        yi_n[0] = vi.x; yi_n[NB - 1] = vi.y;
-        yj_n[0] = vj.x; yj_n[NB - 1] = vj.y;
+        const double2 t2 = *reinterpret_cast<const double2*>(ylane + off);
+        v[0] = t2.x; v[NB - 1] = t2.y;
       } else {
-        yi_n[0] = *reinterpret_cast<const double*>(pi);
-        yj_n[0] = *reinterpret_cast<const double*>(pj);
+        v[0] = *reinterpret_cast<const double*>(ylane + off);
       }
     };
-    fetch(0);
+    auto fetch_y = [&](int p) {
+      const int2 t = tabl[4 * p];
+      ld_y(unsigned(t.x) & 0xffffu, yi_n[0]); ld_y(unsigned(t.x) >> 16, yj_n[0]);
+      ld_y(unsigned(t.y) & 0xffffu, yi_n[1]); ld_y(unsigned(t.y) >> 16, yj_n[1]);
+    };
+    fetch_y(0);
+#pragma unroll
+    for (int cb = 0; cb < CB; ++cb) th[cb] = thl[cb * 8 * 4];
+    const uint32_t th_addr = smem_u32(thl);
+    constexpr int G = 2;                                                // (the last group of an odd CB holds one block)
 #pragma unroll UNR
-    for (int s = 0; s < steps; ++s) {
-      double th[CB], ph[NB];
+    for (int p = 0; p < pairs; ++p) {
+      double ph[2][NB];
 #pragma unroll
-      for (int cb = 0; cb < CB; ++cb) th[cb] = th_n[cb];
+      for (int q = 0; q < 2; ++q)
 #pragma unroll
-      for (int nb = 0; nb < NB; ++nb) ph[nb] = yi_n[nb] * yj_n[nb];
-      fetch(min(s + 1, steps - 1));
+        for (int nb = 0; nb < NB; ++nb) ph[q][nb] = yi_n[q][nb] * yj_n[q][nb];
+      const int pn = min(p + 1, pairs - 1);
+      fetch_y(pn);
 #pragma unroll
-      for (int nb = 0; nb < NB; ++nb)
+      for (int c0 = 0; c0 < CB; c0 += G) {
 #pragma unroll
-        for (int cb = 0; cb < CB; ++cb)
-          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                       : "+d"(acc[nb][cb][0]), "+d"(acc[nb][cb][1])
-                       : "d"(ph[nb]), "d"(th[cb]));
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+            for (int cb = c0; cb < c0 + G && cb < CB; ++cb)
+              asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                           : "+d"(acc[nb][cb][0]), "+d"(acc[nb][cb][1])
+                           : "d"(ph[q][nb]), "d"(q ? th[cb].y : th[cb].x));
+        // (volatile: the compiler otherwise sinks these loads to the end of the loop body, in front of their first use)
+#pragma unroll
+        for (int cb = c0; cb < c0 + G && cb < CB; ++cb)
+          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
+                       : "=d"(th[cb].x), "=d"(th[cb].y)
+                       : "r"(th_addr + uint32_t(pn * KP * 64 + cb * 512)));
+      }
     }
     // ---- the slice is free: start copying this warp's rows of the CTA's next tile behind the epilogue ----
     __syncwarp();

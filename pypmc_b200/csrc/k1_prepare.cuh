@@ -84,12 +84,12 @@ __global__ void __launch_bounds__(256) k1_mma_prepare(const double* __restrict__
                                                       const double* __restrict__ shift, int kl, int KP, int d, int dp,
                                                       int steps, int mode, double* __restrict__ theta_all, int* __restrict__ flag) {
   if (flag[0] != 0 || flag[1] == 0) return;
-  // block b = (component group, slot in the group); theta of group g is [steps][KP][4] at g * steps * KP * 4
+  // block b = (component group, slot in the group); theta of group g is [steps / 2][KP][4][2] (k1m_theta_index) at g * steps * KP * 4
   const int grp = blockIdx.x / KP, slot = blockIdx.x - grp * KP, k = grp * KP + slot, tid = threadIdx.x;
   double* theta = theta_all + size_t(grp) * steps * KP * 4;
   const int nt = tri_len(dp), rl = record_len(dp), F = k1m_features(d);
   if (k >= kl) {                                                        // padding components: theta = 0
-    for (int f = tid; f < steps * 4; f += blockDim.x) theta[(size_t(f >> 2) * KP + slot) * 4 + (f & 3)] = 0.0;
+    for (int f = tid; f < steps * 4; f += blockDim.x) theta[k1m_theta_index(f, KP, slot)] = 0.0;
     return;
   }
   __shared__ double Ts[PMC_MAX_DP * PMC_MAX_DP];                        // dense T, row stride dp
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256) k1_mma_prepare(const double* __restrict__
       v = (r == c) ? m : 2.0 * m;
       ph = ds[r] * ds[c];
     }
-    theta[(size_t(f >> 2) * KP + slot) * 4 + (f & 3)] = v;
+    theta[k1m_theta_index(f, KP, slot)] = v;
     size = fma(fabs(v), ph, size);
   }
 #pragma unroll
