@@ -37,6 +37,8 @@
 
 #include "pmc_common.cuh"
 
+#include <type_traits>
+
 namespace pmc {
 
 constexpr int K2_TK = 16;          // components per lane tile
@@ -295,9 +297,30 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_suffstats(const StatsArgs a)
     const int warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, tq = lane & 3;            // fragment coordinates: A row / B col / C row = g, k index = tq
     const int chunk_f = blockIdx.y % a.fchunks, chunk_c = blockIdx.y / a.fchunks;
-    const int fb_first = (chunk_f * (K2_CONSUMERS / 32) + warp) * FB;     // first feature block of this warp
+    // feature blocks of this CTA [cta_first, cta_first + n_cta), dealt to the 8 warps as evenly as they go: the first `rem`
+    // warps take one more.  Warps w and w + 4 share a scheduler, so the extra blocks land on different schedulers first
+    // (D = 40: 108 blocks = 4 x 14 + 4 x 13, 27 per scheduler; in order 7 x 14 + 10 one scheduler ran 24, the others 28).
+    const int per_cta = (a.nFB + a.fchunks - 1) / a.fchunks, cta_first = chunk_f * per_cta;
+    const int n_cta = max(0, min(per_cta, a.nFB - cta_first));
+    constexpr int NWC = K2_CONSUMERS / 32;
+    const int fb_base = n_cta / NWC, fb_rem = n_cta - fb_base * NWC;
+    // (an FB more than one above the even share -- the instantiated counts are coarse for some CB -- keeps the in-order deal)
+    // and the even deal is only taken where it lowers the busiest scheduler's count (C4: 27 instead of 28; at C2 and C3 both
+    // deals peak at 16 and 8 and the in-order one measured the same or better)
+    int peak_in_order = 0, peak_even = 0;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const int a0 = max(0, min(FB, n_cta - w * FB)), a1 = max(0, min(FB, n_cta - (w + 4) * FB));
+      peak_in_order = max(peak_in_order, a0 + a1);
+      peak_even = max(peak_even, 2 * fb_base + (w < fb_rem ? 1 : 0) + (w + 4 < fb_rem ? 1 : 0));
+    }
+    // (a second copy of the loop only where a block less is worth it: FB >= 8; smaller tiles keep one loop and the in-order deal)
+    constexpr bool K2_EVEN_DEAL = FB >= 8;
+    const bool even_deal = K2_EVEN_DEAL && n_cta >= NWC * (FB - 1) && peak_even < peak_in_order;
+    const int fb_first = cta_first + (even_deal ? warp * fb_base + min(warp, fb_rem) : warp * FB);   // first block of this warp
     const int cb_first = chunk_c * CB, cb_total = KP / 8;
-    const int nfb_w = max(0, min(FB, a.nFB - fb_first));
+    const int nfb_w = even_deal ? min(FB, fb_base + (warp < fb_rem ? 1 : 0))   // (the host picks FB >= ceil(per_cta / 8))
+                                : max(0, min(FB, n_cta - warp * FB));
     // feature f -> the two entries of [y, 1, 0] whose product it is: f = 0: 1*1 (B_k); 1..D: y_i * 1 (m_k); then the
     // lower triangle of y y^T row-major; beyond F: the zero column D+1
     int off_i[FB], off_j[FB];
@@ -305,7 +328,8 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_suffstats(const StatsArgs a)
     for (int fb = 0; fb < FB; ++fb) {
       const int f = (fb_first + fb) * 8 + g;
       int oi = D + 1, oj = D + 1;
-      if (f == 0) { oi = D; oj = D; }
+      if (fb >= nfb_w) { }                             // not this warp's block: the zero column
+      else if (f == 0) { oi = D; oj = D; }
       else if (f <= D) { oi = f - 1; oj = D; }
       else if (f < a.F) {
         const int t = f - 1 - D;
@@ -339,41 +363,44 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_suffstats(const StatsArgs a)
       mbar_wait(&full[s], uint32_t((it / K2_STAGES) & 1));
       const double* Vs = stage0 + s * stage_len;
       const double* Ys = Vs + TN * VS;
-      if (nfb_w > 0) {
-        // no branch inside the step: feature blocks beyond the warp's share multiply the zero column, so every
-        // load of a step can be issued before its first DMMA and the DMMAs go back to back.  One pass = an 8-sample
-        // block = two 4-sample steps (samples 2 tq and 2 tq + 1 of the block are the k index of the first / second
-        // step): CB + 2 FB LDS.128, 2 FB DMUL, 2 CB FB DMMA.
+      // no branch inside the step: every load of a pass can be issued before its first DMMA and the DMMAs go back to back.
+      // One pass = an 8-sample block = two 4-sample steps (samples 2 tq and 2 tq + 1 of the block are the k index of the
+      // first / second step): CB + 2 NF LDS.128, 2 NF DMUL, 2 CB NF DMMA.  NF = the warp's own block count (FB or FB - 1:
+      // no issued work on blocks it does not have); any other count runs all FB slots against the zero column.
+      auto consume = [&](auto nf_tag) {
+        constexpr int NF = decltype(nf_tag)::value;
         const char* vblk = reinterpret_cast<const char*>(Vs);
         const char* yblk = reinterpret_cast<const char*>(Ys);
         for (int n0 = 0; n0 < TN; n0 += 8, vblk += VS * 64, yblk += YS * 64) {
           double2 av[CB];
-          double b0[FB], b1[FB];
+          double b0[NF], b1[NF];
 #pragma unroll
           for (int cb = 0; cb < CB; ++cb) av[cb] = *reinterpret_cast<const double2*>(vblk + cb_off[cb]);
 #pragma unroll
-          for (int fb = 0; fb < FB; ++fb) {
+          for (int fb = 0; fb < NF; ++fb) {
             const double2 yi = *reinterpret_cast<const double2*>(yblk + off_i[fb]);
             const double2 yj = *reinterpret_cast<const double2*>(yblk + off_j[fb]);
             b0[fb] = yi.x * yj.x;
             b1[fb] = yi.y * yj.y;
           }
 #pragma unroll
-          for (int fb = 0; fb < FB; ++fb)
+          for (int fb = 0; fb < NF; ++fb)
 #pragma unroll
             for (int cb = 0; cb < CB; ++cb)
               asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                            : "+d"(acc[cb][fb][0]), "+d"(acc[cb][fb][1])
                            : "d"(av[cb].x), "d"(b0[fb]));
 #pragma unroll
-          for (int fb = 0; fb < FB; ++fb)
+          for (int fb = 0; fb < NF; ++fb)
 #pragma unroll
             for (int cb = 0; cb < CB; ++cb)
               asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                            : "+d"(acc[cb][fb][0]), "+d"(acc[cb][fb][1])
                            : "d"(av[cb].y), "d"(b1[fb]));
         }
-      }
+      };
+      if (K2_EVEN_DEAL && nfb_w == FB - 1) consume(std::integral_constant<int, (K2_EVEN_DEAL ? FB - 1 : FB)>());
+      else if (nfb_w > 0) consume(std::integral_constant<int, FB>());
       mbar_arrive(&empty[s]);                                   // the producer may refill this stage
     }
     // ---- write this CTA's partial block: lane holds Out[8 cb + g][8 fb + 2 tq + e] ----
