@@ -27,9 +27,12 @@
 // blocks of a lane interleaved (slot 2g + nb): the x_i operand of a feature quad is then ONE 128-byte wavefront and one
 // LDS.128 per lane serves both sample blocks (the row-major slice of round 1 took 2 LDS.64 and 4 wavefronts for it;
 // bare loop 86.9 -> 90.6 % of the DMMA peak, profiles/r02b_dmma_feed.md).  The slice is filled by cp.async with the
-// rows of the NEXT tile while the epilogue of the current one runs; x - c is applied in place.  Per feature quad: one
-// table word (byte offsets of the quad's two columns), 2 LDS.128 + NB DMUL for phi, CB LDS.64 for theta, NB x CB
-// DMMAs into 8x8 (sample x component) accumulators; the operands of quad s+1 are fetched before the DMMAs of quad s.
+// rows of the NEXT tile while the epilogue of the current one runs; x - c is applied in place.  The feature quads are
+// taken in PAIRS: per pair one table load (LDS.64: byte offsets of both quads' two columns), 4 LDS.128 + 2 NB DMUL for
+// phi, CB LDS.128 for theta ([pair][component][feature][quad]: both quads' fragments in one load), 2 NB x CB DMMAs
+// into 8x8 (sample x component) accumulators; the y operands of the next pair are fetched before the DMMAs of this
+// one and theta fragments are reloaded in place (an LDS instruction of either width costs the sub-partition about
+// the same DMMA issue time -- scripts/ubench/k1_feed.cu, k2_feed.cu -- so fewer, wider loads: bare loop 89.8 -> 93.9 %).
 // A sample's K log-pdfs end up inside one quad of lanes, so the log-sum-exp is two shuffles deep and the N x K
 // outputs leave as 16-byte stores, two full sectors per quad.  The second pass (rho = exp(lp) w_k / (exp(log q) +
 // tiny), or the VB soft-max with its sum r log r) happens here too, on the log-pdfs still in registers, one sample

@@ -29,6 +29,10 @@
 // v = w rho gamma and [x - shift, 1] and fills a three-stage shared-memory ring; stages are handed over with
 // mbarriers (full / empty), so the consumers never wait on global memory and there is no block-wide barrier
 // in the sample loop.
+// Round 2: the matrix-instruction consumers read a TRANSPOSED, swizzled stage (8-sample blocks, one LDS.128 per operand
+// and two 4-sample steps -- k2_stage / k2_swz below), the producers pull their next tile into L2 ahead of time and
+// issue no FP64 instruction that is not needed (their DMULs queue behind the consumers' DMMAs), and the feature
+// blocks are dealt evenly over the warps where that lowers the busiest scheduler's count.
 // Each CTA writes one partial block; a second tiny kernel adds the partials in CTA order -- no floating-point
 // atomics, so results are reproducible run to run for a given grid.  The default consumer form issues the update as
 // FP64 matrix instructions (DMMA, see the template note below); the DFMA register tile described here is kept

@@ -286,6 +286,11 @@ def _pmc_update(samples, density, weights, latent, rb, mincount, copy, mode, dof
     ds = _as_device_samples(samples, weights, latent)
     _check_arguments(samples, weights, ds.latent, mincount, rb)       # the latent indices that will actually be used
     if copy:
+        if isinstance(density, MixtureDensity) and density._kernel_mode() == mode and density.dim <= _lib.MAX_DIM:
+            # the packed CUDA records are cached per component and shared by copies: form them on the caller's object,
+            # so that a mixture handed in again (or its next copy) does not pay the packing again (1 ms at K = 32)
+            for k in _live_components(density):
+                density.components[k]._packed_record()
         density = _cp(density)
     if not isinstance(density, MixtureDensity) or density._require_mode() != mode:
         raise TypeError("``density`` must be a MixtureDensity with %s components"

@@ -304,10 +304,15 @@ def test_k2_vs_numpy_moments(pm):
                                     (20, 30, 1500, False, True), (40, 20, 1300, True, True), (48, 30, 1200, False, False),
                                     (50, 9, 800, True, False), (100, 12, 700, False, True), (21, 3, 300, True, True),
                                     # 65..128 components: the producer warps' second load path
-                                    (128, 10, 600, True, True), (96, 33, 500, False, False), (72, 20, 900, True, False)]:
+                                    (128, 10, 600, True, True), (96, 33, 500, False, False), (72, 20, 900, True, False),
+                                    # D > 62: the producers' generic path into the transposed stage; gamma over many
+                                    # binades (the table logarithm of k2_colsums, arguments below and above 1)
+                                    (7, 70, 333, True, True), (16, 66, 257, False, False)]:
         x = rng.normal(size=(N, D)) + 2.0
         rho = rng.uniform(size=(N, K))
         gam = rng.uniform(0.5, 2.0, size=(N, K)) if use_g else None
+        if use_g and D == 70:
+            gam = np.exp(rng.uniform(np.log(1e-9), np.log(1e6), size=(N, K)))
         w = rng.uniform(0.5, 1.5, size=N) if use_w else None
         shift = rng.normal(size=D)
         T = D * (D + 1) // 2
