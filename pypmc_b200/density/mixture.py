@@ -35,6 +35,20 @@ class MixtureDensity(ProbabilityDensity):
         assert k == len(self.weights)
         return k
 
+    def __deepcopy__(self, memo):
+        # what copy.deepcopy would build, without its generic walk over the list and the dict (0.4 ms per update at
+        # K = 32): components through their own __deepcopy__, arrays copied flat, anything else deep-copied
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for key, val in self.__dict__.items():
+            if key == "components":
+                new.components = [_deepcopy(c, memo) for c in val]
+            elif isinstance(val, _np.ndarray):
+                new.__dict__[key] = val.copy()
+            else:
+                new.__dict__[key] = _deepcopy(val, memo)
+        return new
+
     def normalize(self):
         """Scale the component weights to sum to one."""
         self.weights /= self.weights.sum()

@@ -86,11 +86,10 @@ def shift_groups(centers, precisions, weights, live, limit=SHIFT_CONDITION_LIMIT
         return (w[:, None] * mus).sum(axis=0) / w.sum()
 
     def worst(idx, c):
-        q = 0.0
-        for k in idx:
-            d = np.abs(np.asarray(centers[k], dtype=float) - c)
-            q = max(q, float(d @ np.abs(precisions[k]) @ d))
-        return q
+        d = np.abs(np.array([centers[k] for k in idx], dtype=float) - c)              # [k, D]
+        p = np.abs(np.array([precisions[k] for k in idx], dtype=float))               # [k, D, D]
+        q = np.einsum("ki,kij,kj->k", d, p, d)
+        return float(np.max(q)) if not np.isnan(q).any() else float("nan")            # (NaN: the caller keeps one group)
 
     c_all = centre(live)
     if not (worst(live, c_all) > limit):          # also taken when the estimate is NaN: one group, like before

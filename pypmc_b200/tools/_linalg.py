@@ -69,8 +69,15 @@ def chol_inv_det_batch(ms):
     if not (_np.abs(ms - mt) <= 1e-8 + 1e-5 * _np.abs(mt)).all():
         raise _np.linalg.LinAlgError("matrix not symmetric")
     low = _np.linalg.cholesky(ms)                       # LinAlgError when a matrix is not positive definite
-    d = ms.shape[1]
-    t = _np.tril(_np.linalg.solve(low, _np.broadcast_to(_np.eye(d), ms.shape)))
+    # T = L^-1 by LAPACK dtrtri per matrix, the routine behind tri_from_chol (same bits as the per-component path; a
+    # batched LU solve against the identity cost 0.45 ms at K = 32, D = 30, K dtrtri calls 0.15 ms)
+    t = _np.empty_like(low)
+    for i in range(low.shape[0]):
+        ti, info = _trtri(low[i], lower=1)
+        if info != 0:
+            raise _np.linalg.LinAlgError("trtri failed with info=%d" % info)
+        t[i] = ti
+    t = _np.tril(t)
     inv = t.transpose(0, 2, 1) @ t
     inv = 0.5 * (inv + inv.transpose(0, 2, 1))
     log_det = 2.0 * _np.log(_np.diagonal(low, axis1=1, axis2=2)).sum(axis=1)
