@@ -706,16 +706,30 @@ int pmcb200_mixture_propose(pmcb200_ctx* c, int64_t n, int d, int k, const doubl
   ProposeArgs a{n, ldx, d, k, means, chol, dofs, static_cast<const int64_t*>(c->pws.p), seed, index0, x, latent};
   const size_t smem = k3_smem_bytes(d, k);
   PMC_REQUIRE(smem <= 200 * 1024, "mixture_propose: too many components for the shared-memory table");
-  static PerDeviceFlag attr_flag;
-  bool& attr_set = attr_flag.here();
-  if (!attr_set) {
-    PMC_CUDA_CHECK(cudaFuncSetAttribute(k3_propose, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
   const int64_t blocks = (n + K3_THREADS - 1) / K3_THREADS;
   const int grid = int(std::min<int64_t>(blocks, int64_t(c->sm_count) * 8));
-  k3_propose<<<grid, K3_THREADS, smem, st>>>(a);
-  PMC_CUDA_CHECK(cudaGetLastError());
+  static PerDeviceFlag attr_flags[6];
+  auto launch = [&](auto kernel, PerDeviceFlag& flag) -> int {
+    bool& attr_set = flag.here();
+    if (!attr_set) {
+      PMC_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set = true;
+    }
+    kernel<<<grid, K3_THREADS, smem, st>>>(a);
+    PMC_CUDA_CHECK(cudaGetLastError());
+    return 0;
+  };
+  // register-resident form up to D = 40 (PMCB200_K3_FORM=smem keeps the shared-memory rows, for comparison runs)
+  static const char* k3_env = getenv("PMCB200_K3_FORM");
+  const bool regs = !(k3_env && std::string(k3_env) == "smem");
+  int rc;
+  if (regs && d <= 8) rc = launch(k3_propose<8>, attr_flags[1]);
+  else if (regs && d <= 16) rc = launch(k3_propose<16>, attr_flags[2]);
+  else if (regs && d <= 24) rc = launch(k3_propose<24>, attr_flags[3]);
+  else if (regs && d <= 32) rc = launch(k3_propose<32>, attr_flags[4]);
+  else if (regs && d <= 40) rc = launch(k3_propose<40>, attr_flags[5]);
+  else rc = launch(k3_propose<0>, attr_flags[0]);
+  if (rc) return rc;
   c->launches++;
   return 0;
 }
