@@ -407,6 +407,53 @@ def test_propose_device_statistics(pm):
     assert bool(torch.isfinite(lq).all())
 
 
+def test_propose_device_forms_agree(pm, tmp_path):
+    """K3's register-resident form (D <= 40, the default) and its shared-memory form (any D; PMCB200_K3_FORM=smem)
+    consume the Philox words and add the products in the same order: the same samples bit for bit.  Also checks the
+    normals of k3_normal2 (own Box-Muller: table logarithm, Taylor sine / cosine) in a dimension where the product
+    runs in registers: whitened draws at D = 30 are iid N(0, 1), tails included."""
+    import subprocess
+    import sys
+    import textwrap
+    from scipy import stats
+    code = textwrap.dedent('''
+        import sys, numpy as np
+        sys.path.insert(0, %r)
+        from pypmc_b200.density.mixture import create_gaussian_mixture, create_t_mixture
+        out = {}
+        for (K, D, student) in [(5, 7, False), (8, 30, False), (4, 40, True), (6, 23, True), (3, 16, False), (2, 1, False)]:
+            rng = np.random.default_rng(K * 100 + D)
+            means = rng.normal(0, 3, size=(K, D))
+            a = rng.normal(0, 1 / np.sqrt(D), size=(K, D, D))
+            covs = a @ a.transpose(0, 2, 1) + 0.5 * np.eye(D)
+            mix = create_t_mixture(means, covs, [4.0] * K) if student else create_gaussian_mixture(means, covs)
+            out["x_%%d_%%d" %% (K, D)] = mix.propose_device(30011, np.random.RandomState(1), seed=5).cpu().numpy()
+            if D == 30:
+                out["means"], out["covs"] = means, covs
+                out["counts"] = np.random.RandomState(1).multinomial(30011, mix.weights)
+        np.savez(sys.argv[1], **out)
+    ''') % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for form in ("regs", "smem"):
+        path = str(tmp_path / ("k3_%s.npz" % form))
+        subprocess.check_call([sys.executable, "-c", code, path], env=dict(os.environ, PMCB200_K3_FORM=form))
+        res[form] = np.load(path)
+    for key in res["regs"].files:
+        if key.startswith("x_"):
+            assert np.isfinite(res["regs"][key]).all()
+            np.testing.assert_array_equal(res["regs"][key], res["smem"][key], err_msg=key)
+    x, means, covs, counts = res["regs"]["x_8_30"], res["regs"]["means"], res["regs"]["covs"], res["regs"]["counts"]
+    lat = np.repeat(np.arange(8), counts)
+    z = np.concatenate([np.linalg.solve(np.linalg.cholesky(covs[k]), (x[lat == k] - means[k]).T).T for k in range(8)])
+    n = len(z)
+    assert np.abs(z.mean(0)).max() < 5.0 / np.sqrt(n)
+    assert np.abs(np.cov(z.T) - np.eye(30)).max() < 6.0 * np.sqrt(2.0 / n)
+    flat = z.ravel()
+    assert stats.kstest(flat[:200000], "norm").pvalue > 1e-4
+    assert abs(stats.kurtosis(flat)) < 0.02                               # 9e5 draws: sd of the estimate 0.005
+    assert 3.5 < np.abs(flat).max() < 6.5                                 # the largest of 9e5 normals sits near 4.9
+
+
 # ------------------------------------------------------------------ config 1: the examples/pmc.py loop end to end
 def test_pmc_example_loop_matches_reference(pm, golden):
     """BASELINE config 1: ImportanceSampler.run + gaussian_pmc every 1000 samples, 10 steps, seeded global mtrand,
