@@ -5,6 +5,8 @@
 //   PAIR = 0: quad at a time, operands of quad s+1 fetched before the DMMAs of quad s (th / th_n double buffer)
 //   PAIR = 1: pair at a time, y / table of the next pair prefetched, theta double-buffered (th / th_n as double2)
 //   PAIR = 2: pair at a time, theta fragments reloaded IN PLACE right after their last DMMA of the pair (no second buffer)
+//   PAIR = 3: PAIR 2 with the row operand y_i reloaded only every second pair (what keeping it in registers along a row of
+//             the triangle would save: no measurable gain at C2 / C3, see the log)
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o k1_feed k1_feed.cu
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -80,8 +82,12 @@ __global__ void __launch_bounds__(NW * 32, 1) k(int steps, int tiles, int D, dou
       double2 th[CB], th_n[PAIR == 1 ? CB : 1];
       auto fetch_y = [&](int p) {
         const int2 t = tabl[4 * p];
-        ld_y(unsigned(t.x) & 0xffffu, yi_n[0]); ld_y(unsigned(t.x) >> 16, yj_n[0]);
-        ld_y(unsigned(t.y) & 0xffffu, yi_n[1]); ld_y(unsigned(t.y) >> 16, yj_n[1]);
+        if (PAIR != 3 || (p & 1) == 0) {                      // PAIR 3: the row operand y_i stays in registers for two pairs
+          ld_y(unsigned(t.x) & 0xffffu, yi_n[0]);
+          ld_y(unsigned(t.y) & 0xffffu, yi_n[1]);
+        }
+        ld_y(unsigned(t.x) >> 16, yj_n[0]);
+        ld_y(unsigned(t.y) >> 16, yj_n[1]);
       };
       fetch_y(0);
 #pragma unroll
@@ -154,7 +160,7 @@ int run(int sms, int D, double* out, double peak) {
   return 0;
 }
 
-#define ALL(CB, NB, D) run<CB, NB, 16, 0>(sms, D, out, peak); run<CB, NB, 16, 1>(sms, D, out, peak); run<CB, NB, 16, 2>(sms, D, out, peak);
+#define ALL(CB, NB, D) run<CB, NB, 16, 2>(sms, D, out, peak); run<CB, NB, 16, 3>(sms, D, out, peak);
 
 int main() {
   cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0)); double* out; CK(cudaMalloc(&out, 64));
