@@ -467,7 +467,8 @@ int pmcb200_suffstats(pmcb200_ctx* c, const double* x, int64_t n, int64_t ldx, i
   const size_t per_row = sizeof(double) * (size_t(a.VS) + a.YS);
   const size_t fixed = sizeof(double) * a.DP4 + 2 * K2_STAGES * sizeof(uint64_t) + 128;
   int tn = int((size_t(210) * 1024 - fixed) / (K2_STAGES * per_row));
-  tn = std::min(96, tn) & ~7;
+  static const char* tn_env = getenv("PMCB200_K2_TN");             // tuning runs: rows per stage (default: at most 96)
+  tn = std::min(tn_env ? std::max(8, atoi(tn_env)) : 96, tn) & ~7;
   PMC_REQUIRE(tn >= 8, "suffstats: K and D too large for the shared-memory pipeline");
   a.tn = tn;
   const size_t smem = K2_STAGES * per_row * tn + fixed;
