@@ -301,16 +301,18 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_suffstats(const StatsArgs a)
     const int warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, tq = lane & 3;            // fragment coordinates: A row / B col / C row = g, k index = tq
     const int chunk_f = blockIdx.y % a.fchunks, chunk_c = blockIdx.y / a.fchunks;
-    // feature blocks of this CTA [cta_first, cta_first + n_cta), dealt to the 8 warps as evenly as they go: the first `rem`
-    // warps take one more.  Warps w and w + 4 share a scheduler, so the extra blocks land on different schedulers first
-    // (D = 40: 108 blocks = 4 x 14 + 4 x 13, 27 per scheduler; in order 7 x 14 + 10 one scheduler ran 24, the others 28).
+    // Feature blocks of this CTA: [cta_first, cta_first + n_cta).  Two ways to deal them to the 8 warps:
+    //   in order -- FB blocks each until they run out (the last warps may hold fewer or none);
+    //   evenly   -- n_cta / 8 each, the first `rem` warps one more; those with FB - 1 run a second copy of the loop.
+    // Warps w and w + 4 share a scheduler, so what counts is the busiest scheduler's total: D = 40 has 108 blocks, in order
+    // 7 x 14 + 10 (schedulers 28, 28, 28, 24), evenly 4 x 14 + 4 x 13 (27 each).  The even deal is taken only where it lowers
+    // that peak (at C2 and C3 both deals peak at 16 and 8, and the in-order one measured the same or better), only for
+    // FB >= 8 (a block less is not worth a second loop copy on small tiles) and only when every warp then holds FB or FB - 1
+    // blocks (the instantiated FB values are coarse for some CB).
     const int per_cta = (a.nFB + a.fchunks - 1) / a.fchunks, cta_first = chunk_f * per_cta;
     const int n_cta = max(0, min(per_cta, a.nFB - cta_first));
     constexpr int NWC = K2_CONSUMERS / 32;
     const int fb_base = n_cta / NWC, fb_rem = n_cta - fb_base * NWC;
-    // (an FB more than one above the even share -- the instantiated counts are coarse for some CB -- keeps the in-order deal)
-    // and the even deal is only taken where it lowers the busiest scheduler's count (C4: 27 instead of 28; at C2 and C3 both
-    // deals peak at 16 and 8 and the in-order one measured the same or better)
     int peak_in_order = 0, peak_even = 0;
 #pragma unroll
     for (int w = 0; w < 4; ++w) {
@@ -318,7 +320,6 @@ __global__ void __launch_bounds__(K2_THREADS, 1) k2_suffstats(const StatsArgs a)
       peak_in_order = max(peak_in_order, a0 + a1);
       peak_even = max(peak_even, 2 * fb_base + (w < fb_rem ? 1 : 0) + (w + 4 < fb_rem ? 1 : 0));
     }
-    // (a second copy of the loop only where a block less is worth it: FB >= 8; smaller tiles keep one loop and the in-order deal)
     constexpr bool K2_EVEN_DEAL = FB >= 8;
     const bool even_deal = K2_EVEN_DEAL && n_cta >= NWC * (FB - 1) && peak_even < peak_in_order;
     const int fb_first = cta_first + (even_deal ? warp * fb_base + min(warp, fb_rem) : warp * FB);   // first block of this warp
