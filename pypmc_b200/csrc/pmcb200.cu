@@ -148,7 +148,15 @@ static bool host_is_pinned(const void* p) {
 }
 
 static int copy_threads() {
-  static const int n = std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
+  // PMCB200_COPY_THREADS overrides; default: half the hardware threads, at most 8.  Measured on the 16-vCPU GPU box
+  // (scripts/bench_pageable.py, 4e6 x 30 pageable rows through multi_evaluate): 4 threads 24.8 GB/s, 8 threads 32.4,
+  // 12: 30.6, 16: 28.3, 24: 25.6 -- the host's memory system, not the thread count, is what stops short of the
+  // ~55 GB/s the PCIe link takes from pinned memory
+  static const int n = [] {
+    const char* env = getenv("PMCB200_COPY_THREADS");
+    if (env && atoi(env) > 0) return std::min(64, atoi(env));
+    return int(std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2)));
+  }();
   return n;
 }
 
