@@ -27,6 +27,8 @@ CASES = {
     "c3_vb": (10_000_000, 64, 20, _lib.MODE_VB, ("resp", "lp")),
     "c3_vb_r": (10_000_000, 64, 20, _lib.MODE_VB, ("resp",)),          # E-step without materialising log_rho
     "c3_eval": (10_000_000, 64, 20, _lib.MODE_GAUSS, ("logq",)),
+    "c3_vb_eval": (10_000_000, 64, 20, _lib.MODE_VB, ("logq",)),       # VB scalars, no N x K output: the loop with two sample blocks
+    "c3_vb_lp": (10_000_000, 64, 20, _lib.MODE_VB, ("lp",)),           # normalised log rho only
     "c4_t_eval": (5_000_000, 16, 40, _lib.MODE_STUDENT_T, ("logq",)),
     "c4_t_rho": (5_000_000, 16, 40, _lib.MODE_STUDENT_T, ("logq", "resp", "aux")),
     # beyond the shared-memory residency of theta: component groups (k1_mma_eval launched per group)
