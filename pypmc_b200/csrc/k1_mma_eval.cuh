@@ -456,6 +456,7 @@ __global__ void __launch_bounds__(NW * 32, 1) k1_mma_eval(const MmaArgs ma) {
         const double2 c2 = *reinterpret_cast<const double2*>(scl + S2 * KP + 8 * cb);
         const double2 c3 = *reinterpret_cast<const double2*>(scl + S3 * KP + 8 * cb);
         const double2 c4 = *reinterpret_cast<const double2*>(scl + S4 * KP + 8 * cb);
+        const bool student = a.mode == MODE_STUDENT_T, want_aux = a.aux_out != nullptr;
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) {
           double l[2], ax[2];
@@ -464,14 +465,12 @@ __global__ void __launch_bounds__(NW * 32, 1) k1_mma_eval(const MmaArgs ma) {
             const double c0e = e ? c0.y : c0.x, c1e = e ? c1.y : c1.x, c2e = e ? c2.y : c2.x, c3e = e ? c3.y : c3.x,
                          c4e = e ? c4.y : c4.x;
             const double q = clamp0(acc[nb][cb][e]);
-            if (a.mode == MODE_STUDENT_T) {
-              double t = q * c2e;                                                        // student_t.pyx:159-164
-              t += 1.0;
+            if (student) {
+              double t = fma(q, c2e, 1.0);                                               // student_t.pyx:159-164
               // 1 <= t < 2^64 always, unless q is non-finite or absurd: then the library logarithm
               t = (unsigned(__double2hiint(t)) - 0x3ff00000u < 0x04000000u) ? log_tab(t, ltab) : log_cold(t);
-              t *= c1e;
-              l[e] = t + c0e;
-              ax[e] = a.aux_out ? c4e * rcp_pos(c3e + q) : 0.0;                          // gamma_nk, pmc.pyx:610
+              l[e] = fma(t, c1e, c0e);
+              ax[e] = want_aux ? c4e * rcp_pos(c3e + q) : 0.0;                           // gamma_nk, pmc.pyx:610
             } else {
               ax[e] = c3e + c4e * q;                                                     // variational.pyx:798
               l[e] = c0e + 0.5 * (c1e - c2e - ax[e]);                                    // variational.pyx:691
