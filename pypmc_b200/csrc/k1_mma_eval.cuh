@@ -147,6 +147,40 @@ __device__ __forceinline__ double log_tab(double x, const double* __restrict__ t
   return (p + tab[128 + j]) + tab[256 + ((hi >> 20) - 1023)];
 }
 static __device__ __noinline__ double log_cold(double x) { return log(x); }
+// ln(x) for any positive normal x (else the library function, out of line): log_tab's reduction with the exponent term
+// formed by two FMAs (ln 2 = 44-bit head + tail, e * head exact), so arguments below 1 need no table entry -- the sum of
+// the log-sum-exp lies in (0, K].  10 FP64 instructions in a dependent chain where the library logarithm has ~25;
+// absolute error <= 2e-16 (1 + |ln x|) (tests/test_device_math_cpu.py emulates the same sequence against np.log).
+__device__ __forceinline__ double log_any(double x, const double* __restrict__ tab) {
+  const int hi = __double2hiint(x);
+  if (unsigned(hi) - 0x00100000u >= 0x7fe00000u) return log_cold(x);   // zero, subnormal, negative, inf, nan
+  const int j = (hi >> 13) & 127;
+  const double e = double((hi >> 20) - 1023);
+  const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
+  const double r = fma(m, tab[j], -1.0);
+  double u = fma(r, -1.66666666666666657e-01, 2.00000000000000011e-01);
+  u = fma(r, u, -0.25);
+  u = fma(r, u, 3.33333333333333315e-01);
+  u = fma(r, u, -0.5);
+  const double p = fma(r * r, u, r);
+  return fma(e, 0x1.62e42fefa38p-1, (p + tab[128 + j]) + e * 0x1.ef35793c7673p-45);
+}
+// ln(x) with RELATIVE accuracy next to 1 (VB: sum = 1 + eps for a sample with one responsible component, ln r of that
+// component is -ln(sum) ~ -eps, and sum_n r ln r adds 1e5 such terms): x - 1 is exact for x in [1, 2), and below 2^-7 the
+// series s - s^2/2 + ... + s^7/7 has a truncation of s^7/8 <= 2^-52 relative; everything else goes to log_any, whose
+// absolute error of ~1e-16 is then <= 1e-14 of the result.
+__device__ __forceinline__ double log_near1(double x, const double* __restrict__ tab) {
+  const double s = x - 1.0;
+  if (s >= 0.0 && s < 0x1p-7) {
+    double u = fma(s, 1.42857142857142849e-01, -1.66666666666666657e-01);
+    u = fma(s, u, 2.00000000000000011e-01);
+    u = fma(s, u, -0.25);
+    u = fma(s, u, 3.33333333333333315e-01);
+    u = fma(s, u, -0.5);
+    return fma(s * s, u, s);
+  }
+  return log_any(x, tab);
+}
 // 1 / x for normal positive x: hardware seed (rcp.approx.ftz.f64, ~2^-23) and two Newton steps, 4 DFMA
 __device__ __forceinline__ double rcp_pos(double x) {
   double y;
@@ -647,7 +681,11 @@ __global__ void __launch_bounds__(NW * 32, 1) k1_mma_eval(const MmaArgs ma) {
         }
         return;
       }
-      const double ls = log(sum);
+      // ln(sum): the table logarithm in the mixture modes (the same function in every instantiation: same bits of log q).
+      // VB: sum = 1 + eps for a sample with one responsible component, ln r of that component IS -ln(sum) ~ -eps, and
+      // sum_n r ln r adds 1e5 such terms -- the table form's absolute error of ~1e-16 is systematic near 1 (one table
+      // entry) and showed up as 2e-12 in the bound's q_Z term (contract 1e-10 relative): log_near1 has a series there.
+      const double ls = (a.mode == MODE_VB) ? log_near1(sum, ltab) : log_any(sum, ltab);
       lq = ls + m;                                                      // _regularize.pyx:81
       if (writer) {
         const double w_n = a.sw ? __ldg(a.sw + row) : 1.0;
@@ -656,7 +694,8 @@ __global__ void __launch_bounds__(NW * 32, 1) k1_mma_eval(const MmaArgs ma) {
         if (a.mode != MODE_VB) part_a += w_n * lq;                      // pmc.pyx:388-391
       }
       if constexpr (SECOND) {
-        f0 = 1.0 / sum;                                                 // variational.pyx:728-755 (and rho below)
+        // 1 / sum: hardware seed + two Newton steps for a positive normal sum (5 instructions, <= 1 ulp), else the division
+        f0 = (unsigned(__double2hiint(sum)) - 0x00100000u < 0x7fe00000u) ? rcp_pos(sum) : 1.0 / sum;   // variational.pyx:728-755 (and rho below)
         f1 = -ls;
       } else if (ma.rowstat && writer) {                                // for k1_finish
         ma.rowstat[2 * row] = m;

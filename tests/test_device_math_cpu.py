@@ -103,3 +103,26 @@ def test_k3_box_muller_matches_library_on_the_same_bits():
     zr = np.concatenate([ref * np.cos(2 * np.pi * u2), ref * np.sin(2 * np.pi * u2)])
     assert np.max(np.abs(z - zr)) < 1e-13
     assert abs(z.mean()) < 5.0 / np.sqrt(len(z)) and abs(z.var() - 1.0) < 6.0 * np.sqrt(2.0 / len(z))
+
+
+def test_vb_logarithm_next_to_one_is_relative():
+    """`log_near1` (k1_mma_eval.cuh): ln(sum) for the VB soft-max, where sum = 1 + eps for a sample with one responsible
+    component and ln r of that component is -ln(sum): the series below 2^-7 keeps RELATIVE accuracy (the table form's
+    ~1e-16 absolute error, systematic next to 1, was worth 2e-12 in sum_n r ln r at N = 1.2e5)."""
+    src = open(os.path.join(CSRC, "k1_mma_eval.cuh")).read()
+    body = src[src.index("double log_near1("):]
+    body = body[:body.index("return log_any")]
+    coef = [float(v) for v in re.findall(r"-?\d\.\d+e[+-]\d+|-0\.25|-0\.5", body)]
+    np.testing.assert_allclose(coef, [1 / 7, -1 / 6, 1 / 5, -0.25, 1 / 3, -0.5], rtol=1e-15)
+    rng = np.random.default_rng(2)
+    s = np.concatenate([np.exp(rng.uniform(np.log(1e-18), np.log(2.0 ** -7), size=200_000)), [0.0, 2.0 ** -7 * (1 - 1e-16)]])
+    x = 1.0 + s
+    s = x - 1.0                                                  # what the kernel sees (exact for x in [1, 2))
+    u = s * coef[0] + coef[1]
+    for c in coef[2:]:
+        u = s * u + c
+    got = (s * s) * u + s
+    ref = np.log1p(s)
+    ok = ref > 0
+    assert np.max(np.abs(got[ok] - ref[ok]) / ref[ok]) < 5e-16
+    assert (got[s == 0.0] == 0.0).all()
